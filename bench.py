@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py - CWT power output points/s (T x F x ch) on B200, BASELINE.json's metric.
+
+Workload (config.workload): BASELINE.json configs[1] - 64-channel EEG, 600 000 samples per
+channel at 1 kHz, Morse(17.5, 3) power at 1..100 Hz, fp32 (the configuration the metric is
+quoted on; 15.4 GB of fp32 output per GPU, fits one B200).  One "step" = one pass of the hot
+path over the 64 channels of this rank (forward FFTs, spectrum generation, inverse FFTs, |z|^2).
+Multi-GPU: every rank owns its own 64 channels (weak scaling, no collective on the data path).
+
+Prints ONE JSON line on rank 0 (see the task contract): value = device-resident throughput,
+e2e = the same through the C ABI's host-buffer call (H2D and D2H inside the timed region),
+roofline = algorithmic HBM bytes / measured duration of the path's kernels vs MEASURED_PEAKS.json,
+cpu_baseline = the numpy oracle (port of the reference) timed on this box's host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference]
+                  [--workload cfg2|cfg3|cfg4] [--dtype f32|f64]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cwt_power_output_points_per_sec"
+UNIT = "points/s"
+
+WORKLOADS = {
+    # name: (family, kwargs, n_signals, n, freqs, baseline)
+    "cfg2": dict(desc="cfg2: 64 ch x 600000 samples @1 kHz, Morse(17.5,3) power, freqs 1-100",
+                 kind="morse", S=64, N=600000, freqs=np.arange(1, 101.0), baseline=None),
+    "cfg3": dict(desc="cfg3: 306 ch x 200 epochs x 1500 samples @1 kHz, Morlet(7) power + zscore[0,0.2s], freqs 1-100",
+                 kind="morlet", S=306 * 200, N=1500, freqs=np.arange(1, 101.0), baseline=("zscore", 0.0, 0.2)),
+    "cfg4": dict(desc="cfg4: 32 ch x 2^20 samples, Morse power, freqs 1-128",
+                 kind="morse", S=32, N=1 << 20, freqs=np.arange(1, 129.0), baseline=None),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.15:
+                continue
+            parts = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except Exception:
+                continue
+            for name, val in zip(self.NAMES, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs (oracle = port of the reference; the ONLY place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------
+def _oracle_family(wl):
+    import cwt_oracle as orc
+    if wl["kind"] == "morse":
+        return orc.Family("morse", sfreq=1000.0, b=17.5, r=3.0)
+    return orc.Family("morlet", sfreq=1000.0, sigma=7.0)
+
+
+def _oracle_one(args):
+    """One signal through the reference algorithm, cold call (spectra rebuilt, reuse=False)."""
+    import cwt_oracle as orc
+    kind, n, freqs, seed, baseline = args
+    fam = orc.Family(kind, sfreq=1000.0) if kind == "morse" else orc.Family("morlet", sfreq=1000.0, sigma=7.0)
+    x = np.random.default_rng(seed).standard_normal(n)
+    p = orc.power(fam, x, freqs)
+    if baseline is not None:
+        p = orc.baseline_rows(p, 1000.0, baseline[1], baseline[2], baseline[0])
+    return float(p[0, 0])
+
+
+def cpu_sample(wl, workers, signals_per_worker, freqs):
+    """Time `workers * signals_per_worker` signals of the workload on host cores; returns (points/s, desc)."""
+    from multiprocessing import get_context
+    jobs = [(wl["kind"], wl["N"], freqs, 1000 + i, wl["baseline"]) for i in range(workers * signals_per_worker)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        for j in jobs:
+            _oracle_one(j)
+    else:
+        with get_context("fork").Pool(workers) as pool:
+            pool.map(_oracle_one, jobs, chunksize=signals_per_worker)
+    dt = time.perf_counter() - t0
+    pts = len(jobs) * len(freqs) * wl["N"]
+    return pts / dt, dt
+
+
+def sample_shape(wl):
+    """Bounded CPU sample: ~1e8 output points per worker-step (a few seconds each)."""
+    n, F = wl["N"], len(wl["freqs"])
+    if n * F > 2.5e7:       # long rows: one signal, a quarter of the frequencies
+        fr = wl["freqs"][:: max(1, F // 25)]
+        return 1, fr
+    per = max(1, int(2e7 // (n * F)))
+    return per, wl["freqs"]
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = max(1, min(os.cpu_count() or 1, 16))
+    per, fr = sample_shape(wl)
+    for _ in range(args.warmup):
+        cpu_sample(wl, workers, per, fr)
+    t0 = time.perf_counter()
+    pts = 0
+    for _ in range(args.steps):
+        v, dt = cpu_sample(wl, workers, per, fr)
+        pts += workers * per * len(fr) * wl["N"]
+    total = time.perf_counter() - t0
+    value = pts / total
+    sample = "%d signals x %d freqs x %d samples per step (%s), %d worker processes, cold calls" % (
+        workers * per, len(fr), wl["N"], wl["desc"].split(":")[0], workers)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def run_graft(args, wl):
+    import torch
+    import torch.distributed as dist
+    import ninwavelets_b200 as nw
+    from ninwavelets_b200 import _backend as be
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    f32 = args.dtype == "f32"
+    tdt = torch.float32 if f32 else torch.float64
+    S, N, freqs = wl["S"], wl["N"], wl["freqs"]
+    F = len(freqs)
+
+    # synthetic signals, generated on the host and made resident before timing (value),
+    # kept on the host (pinned) for the end-to-end leg
+    rng = np.random.default_rng(2 + rank)
+    e2e_S = min(S, max(1, int((4 << 30) // (F * N * (4 if f32 else 8)))))   # <= 4 GiB of output per e2e step
+    host_x = torch.empty((S, N), dtype=tdt).pin_memory()
+    hx = host_x.numpy()
+    t = np.arange(N) / 1000.0
+    for s in range(S):
+        hx[s] = rng.standard_normal(N)
+        if wl["kind"] == "morse":
+            for f0 in (10.0, 40.0, 60.0):
+                hx[s] += np.sin(2 * np.pi * f0 * t + rng.uniform(0, 2 * np.pi))
+    x = host_x.to(dev)
+
+    ctor = nw.Morse if wl["kind"] == "morse" else nw.Morlet
+    obj = ctor(1000, cuda=True, dtype="float32" if f32 else "float64", device=local)
+    obj.make_fft_wavelets(freqs, N / 1000.0)
+    plan = obj._plan
+    info = plan.info()
+    bl = (0, 0, 0)
+    if wl["baseline"] is not None:
+        from ninwavelets_b200.base import _window
+        lo, hi = _window(N, 1000.0, wl["baseline"][1], wl["baseline"][2])
+        bl = (be.BASELINE_MODES[wl["baseline"][0]], lo, hi)
+    out = torch.empty((S, F, N), dtype=tdt, device=dev)
+
+    def step():
+        plan.transform_device(x, be.OUT_POWER, *bl, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = be.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = be.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    points_per_step = S * F * N * world
+    value = points_per_step * args.steps / (ms * 1e-3)
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+
+    # ---- kernel-class timing for the roofline (separate pass, CUDA events around every launch
+    #      on the launching stream; same workload, not part of `value`) ----------------------------
+    be.profile_enable(True)
+    step()
+    torch.cuda.synchronize()
+    prof = be.profile_read()
+    be.profile_enable(False)
+    real_b = 4 if f32 else 8
+    alg_bytes_step = S * N * (F + 1) * real_b              # write one real per point + read each sample once
+    kern = {k: v for k, v in prof.items() if v["launches"]}
+    tot_ms = sum(v["ms"] for v in kern.values())
+    dominant = max(kern, key=lambda k: kern[k]["ms"])
+    peak, peak_src = peaks()
+    achieved = alg_bytes_step / (tot_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src,
+        "kernel": "all kernels of one step (the path is %s); dominant class %s" % (
+            "one fused kernel" if info["path"] == "short" else "the inverse passA+passB pair per row group", dominant),
+        "algorithmic_bytes_per_step": alg_bytes_step,
+        "kernel_ms_per_step": tot_ms,
+        "classes": {k: {"ms": round(v["ms"], 4), "launches": v["launches"], "share": v["ms"] / tot_ms,
+                        "avg_launch_ms": v["ms"] / v["launches"]} for k, v in kern.items()},
+    }
+
+    # ---- end to end through the C ABI's host-buffer entry point ---------------------------------
+    host_out = torch.empty((e2e_S, F, N), dtype=tdt).pin_memory()
+    hin = hx[:e2e_S]
+    hout = host_out.numpy()
+    plan.transform_host(hin, be.OUT_POWER, *bl, out=hout)        # warm-up (allocates staging)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.transform_host(hin, be.OUT_POWER, *bl, out=hout)
+    torch.cuda.synchronize()
+    e_dt = time.perf_counter() - t0
+    if world > 1:
+        tms = torch.tensor([e_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e_dt = float(tms.item())
+    e2e = {"value": e2e_S * F * N * world * e2e_steps / e_dt, "unit": UNIT,
+           "h2d_bytes_per_step": int(e2e_S * N * real_b), "d2h_bytes_per_step": int(e2e_S * F * N * real_b),
+           "steps": e2e_steps, "signals_per_step": e2e_S,
+           "api": "nwcwt_transform_host (pinned host buffers; chunked H2D -> kernels -> D2H on two streams)"}
+
+    # ---- parity spot check of the timed output against the oracle (not timed) -------------------
+    parity = None
+    cpu = None
+    if rank == 0:
+        import cwt_oracle as orc
+        fam = _oracle_family(wl)
+        sub = freqs[:: max(1, F // 4)][:4] if N > 100000 else freqs
+        xs = hx[0].astype(np.float64)
+        ref = orc.power(fam, xs, sub)
+        if wl["baseline"] is not None:
+            ref = orc.baseline_rows(ref, 1000.0, wl["baseline"][1], wl["baseline"][2], wl["baseline"][0])
+        idx = [int(np.nonzero(freqs == f)[0][0]) for f in sub]
+        got = out[0, idx].double().cpu().numpy()
+        num = np.sqrt(((got - ref) ** 2).sum(axis=1))
+        den = np.sqrt((ref ** 2).sum(axis=1))
+        parity = {"rows_checked": len(idx), "max_row_rel_l2": float((num / np.maximum(den, 1e-2 * den.max())).max())}
+        # bounded CPU sample of the same workload on this box's host cores (single process = as shipped)
+        per, fr = sample_shape(wl)
+        v, dt = cpu_sample(wl, 1, per, fr)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d signal(s) x %d freqs x %d samples, cold call, %.1f s" % (per, len(fr), N, dt),
+               "host_cpus": os.cpu_count()}
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": wl["desc"], "signals_per_gpu": S, "n": N, "n_freqs": F, "path": info["path"],
+                       "split": [info["n1"], info["n2"]], "radices": info["radices"], "batch": info["batch"],
+                       "l2": "inputs+outputs per step (%.1f GB) far exceed the 126 MB L2" % (
+                           (S * N * (F + 1) * real_b) / 1e9)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_spot_check": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_graft(args, wl)
+
+
+if __name__ == "__main__":
+    main()

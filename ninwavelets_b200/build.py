@@ -1,0 +1,60 @@
+"""In-tree build of libnwcwt.so for sm_100a (nvcc cross-compiles without a GPU).
+
+The transform kernels are instantiated per (kernel group, precision) in their own .cu files
+and compiled in parallel; nwcwt.cu holds the C ABI."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libnwcwt.so")
+SOURCES = ["nwcwt.cu", "k_short_f32.cu", "k_short_f64.cu", "k_passA_f32.cu", "k_passA_f64.cu",
+           "k_passB_f32.cu", "k_passB_f64.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC"]
+
+
+def _deps():
+    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    d.append(os.path.join(os.path.dirname(HERE), "include", "nwcwt.h"))
+    return d
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+    newest = max(os.path.getmtime(d) for d in _deps())
+    if os.path.isfile(obj) and os.path.getmtime(obj) >= newest:
+        return obj, ""
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stdout))
+    return obj, r.stdout
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    newest = max(os.path.getmtime(d) for d in _deps())
+    if not force and os.path.isfile(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 2)) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    cmd = [os.environ.get("NVCC", "nvcc"), "-shared", "-o", LIB] + [o for o, _ in results]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

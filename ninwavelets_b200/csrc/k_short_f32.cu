@@ -1,0 +1,2 @@
+#define NW_REAL float
+#include "nw_kern_short.cuh"

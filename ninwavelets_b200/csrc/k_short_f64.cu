@@ -1,0 +1,2 @@
+#define NW_REAL double
+#include "nw_kern_short.cuh"

@@ -1,0 +1,18 @@
+// Launch interface between the translation units of libnwcwt.so.  The kernels are
+// instantiated per (precision, kernel group) in their own .cu files so that ptxas
+// runs on them in parallel; nwcwt.cu (C ABI, plans) only sees these functions.
+#pragma once
+#include <cuda_runtime.h>
+#include "nw_kernels.cuh"
+
+namespace nw {
+template <typename T> cudaError_t prepare_short();
+template <typename T> cudaError_t prepare_passA();
+template <typename T> cudaError_t prepare_passB();
+template <typename T>
+cudaError_t launch_short(const ShortParams<T>& P, unsigned grid, int nthr, size_t smem, cudaStream_t s);
+template <typename T>
+cudaError_t launch_passA(int dir, const LongParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+template <typename T>
+cudaError_t launch_passB(int dir, const LongParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+}  // namespace nw

@@ -1,0 +1,634 @@
+// libnwcwt.so - C ABI (include/nwcwt.h) over the sm_100a kernels.
+//
+// Replaces, on the device, WaveletBase.make_fft_wavelets / cwt / abs / power
+// (reference base.py:258-279, 378-443), Baseline (base.py:46-68) applied per
+// (signal, frequency) row, and the cupy branch (base.py:236-247, 398-404).
+// There is no CPU path here: without a CUDA device every compute entry point
+// fails with NWCWT_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nwcwt.h"
+#include "nw_common.h"
+#include "nw_fft.cuh"
+#include "nw_family.cuh"
+#include "nw_kernels.cuh"
+#include "nw_plan.h"
+#include "nw_launch.h"
+
+using namespace nw;
+
+// ---------------------------------------------------------------------------------
+// small kernels that live in this translation unit (the transform kernels are in k_*.cu)
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(512) nwcwt_baseline_rows_kernel(T* rows, long long N, int mode, int lo, int hi) {
+    __shared__ double sh[2];
+    baseline_rows_body<T>(rows, N, mode, lo, hi, sh, blockIdx.x, threadIdx.x, blockDim.x);
+}
+
+// Spectrum bank for inspection: one thread per (frequency, bin).
+template <typename T>
+__global__ void __launch_bounds__(256) nwcwt_bank_kernel(SpecParams<T> sp, cx<T>* bank, int F, long long N) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (i >= N || f >= F) return;
+    const FreqRec r = sp.rec[f];
+    cx<T> v = mk<T>((T)0, (T)0);
+    if (i >= r.lo && i < r.hi) v = spec_times<T>(sp, r, f, (int)i, mk<T>((T)1, (T)0));
+    bank[(size_t)f * (size_t)N + (size_t)i] = v;
+}
+
+// Epoch reductions (mneutils.py:53-55 mean of power, :68-71 inter-trial coherence).
+template <typename T>
+__global__ void __launch_bounds__(256) nwcwt_reduce_kernel(const void* in, T* out, long long E, long long count, int kind) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (kind == 0) {
+        const T* p = (const T*)in;
+        T acc = 0;
+        for (long long e = 0; e < E; ++e) acc += p[(size_t)e * (size_t)count + (size_t)i];
+        out[i] = acc / (T)E;
+    } else {
+        const cx<T>* p = (const cx<T>*)in;
+        T ax = 0, ay = 0;
+        for (long long e = 0; e < E; ++e) {
+            const cx<T> z = p[(size_t)e * (size_t)count + (size_t)i];
+            const T a = nw_hypot(z.x, z.y);
+            ax += z.x / a;
+            ay += z.y / a;
+        }
+        out[i] = nw_hypot(ax / (T)E, ay / (T)E);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// plan object
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(NWCWT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+struct nwcwt_plan {
+    HostPlan hp;
+    bool on_device = false;
+    // device tables
+    void *d_tw = nullptr, *d_twA = nullptr, *d_twB = nullptr, *d_twH = nullptr, *d_twL = nullptr;
+    void* d_rec = nullptr;
+    void* d_table = nullptr;
+    // host-call resources
+    void* h_in_dev[2] = {nullptr, nullptr};
+    void* h_out_dev[2] = {nullptr, nullptr};
+    void* h_ws[2] = {nullptr, nullptr};
+    size_t h_in_bytes = 0, h_out_bytes = 0, h_ws_bytes = 0;
+    long long h_chunk = 0;
+    cudaStream_t h_stream[2] = {nullptr, nullptr};
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- launch accounting / optional per-class event timing (bench.py) -----------------------------
+#include <atomic>
+#include <mutex>
+static std::atomic<long long> g_launches{0};
+static bool g_profile = false;
+static std::mutex g_prof_mu;
+struct ProfEvent { cudaEvent_t a, b; int cls; };
+static std::vector<ProfEvent> g_prof_events;
+static double g_prof_ms[6] = {0, 0, 0, 0, 0, 0};
+static long long g_prof_n[6] = {0, 0, 0, 0, 0, 0};
+
+struct LaunchScope {   // counts one launch; with profiling on, brackets it with events on `stream`
+    cudaStream_t stream;
+    ProfEvent ev;
+    bool timed;
+    LaunchScope(int cls, cudaStream_t s) : stream(s), timed(g_profile) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (timed) {
+            ev.cls = cls;
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+            cudaEventRecord(ev.a, stream);
+        }
+    }
+    ~LaunchScope() {
+        if (timed) {
+            cudaEventRecord(ev.b, stream);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            g_prof_events.push_back(ev);
+        }
+    }
+};
+
+template <typename T>
+static void fill_twiddles(std::vector<cx<T>>& v, long long count, long long P, long long step) {
+    // v[j] = exp(+2 pi i (j*step) / P), evaluated in long double
+    v.resize((size_t)count);
+    const long double tp = 6.283185307179586476925286766559005768L;
+    for (long long j = 0; j < count; ++j) {
+        const long long m = (j * step) % P;
+        const long double a = tp * (long double)m / (long double)P;
+        v[(size_t)j].x = (T)cosl(a);
+        v[(size_t)j].y = (T)sinl(a);
+    }
+}
+
+template <typename T>
+static int upload_tw(void** dptr, long long count, long long P, long long step) {
+    std::vector<cx<T>> v;
+    fill_twiddles<T>(v, count, P, step);
+    CUDA_TRY(cudaMalloc(dptr, v.size() * sizeof(cx<T>)));
+    CUDA_TRY(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <typename T>
+static int ensure_device_t(nwcwt_plan* pl) {
+    HostPlan& hp = pl->hp;
+    CUDA_TRY(cudaSetDevice(hp.device));
+    if (pl->on_device) return 0;
+    int rc;
+    if (hp.path == 0) {
+        if ((rc = upload_tw<T>(&pl->d_tw, hp.N, hp.N, 1))) return rc;
+    } else {
+        if ((rc = upload_tw<T>(&pl->d_twA, hp.N1, hp.N1, 1))) return rc;
+        if ((rc = upload_tw<T>(&pl->d_twB, hp.N2, hp.N2, 1))) return rc;
+        const long long nL = 1LL << hp.lb, nH = (hp.N + nL - 1) / nL;
+        if ((rc = upload_tw<T>(&pl->d_twL, nL, hp.N, 1))) return rc;
+        if ((rc = upload_tw<T>(&pl->d_twH, nH, hp.N, nL))) return rc;
+    }
+    if (hp.F > 0) {
+        CUDA_TRY(cudaMalloc(&pl->d_rec, sizeof(FreqRec) * hp.F));
+        CUDA_TRY(cudaMemcpy(pl->d_rec, hp.rec.data(), sizeof(FreqRec) * hp.F, cudaMemcpyHostToDevice));
+    }
+    if (hp.family == FAM_TABLE) {
+        const size_t cnt = (size_t)hp.F * (size_t)hp.table_len;
+        std::vector<cx<T>> t(cnt);
+        for (size_t i = 0; i < cnt; ++i) {
+            t[i].x = (T)hp.table[2 * i];
+            t[i].y = (T)hp.table[2 * i + 1];
+        }
+        CUDA_TRY(cudaMalloc(&pl->d_table, cnt * sizeof(cx<T>)));
+        CUDA_TRY(cudaMemcpy(pl->d_table, t.data(), cnt * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    }
+    // opt in to large dynamic shared memory
+    if (hp.path == 0) {
+        CUDA_TRY(prepare_short<T>());
+    } else {
+        CUDA_TRY(prepare_passA<T>());
+        CUDA_TRY(prepare_passB<T>());
+    }
+    pl->on_device = true;
+    return 0;
+}
+
+static int ensure_device(nwcwt_plan* pl) {
+    return pl->hp.dtype == NWCWT_F32 ? ensure_device_t<float>(pl) : ensure_device_t<double>(pl);
+}
+
+template <typename T>
+static SpecParams<T> make_spec(const nwcwt_plan* pl) {
+    const HostPlan& hp = pl->hp;
+    SpecParams<T> sp;
+    sp.family = hp.family;
+    sp.grid_off = hp.grid_off;
+    sp.df = hp.df;
+    sp.p0 = hp.p0;
+    sp.p1 = hp.p1;
+    sp.p2 = hp.family == FAM_MORSE ? hp.p0 / hp.p1 : hp.p2;   // (self.b / self.r), wavelets.py:72
+    sp.norm = (T)(1.0 / (double)hp.N);                          // 1/N of ifft, base.py:406
+    sp.rec = (const FreqRec*)pl->d_rec;
+    sp.table = (const cx<T>*)pl->d_table;
+    sp.table_len = hp.table_len;
+    return sp;
+}
+
+// ---------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------
+static int device_sms(int device) {
+    static int cached[64] = {0};
+    if (device < 64 && cached[device]) return cached[device];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (device < 64) cached[device] = n;
+    return n;
+}
+
+template <typename T>
+static int launch_short(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
+                        int bl, long long blo, long long bhi, cudaStream_t stream, bool forward_only) {
+    const HostPlan& hp = pl->hp;
+    ShortParams<T> P;
+    memset(&P, 0, sizeof(P));
+    P.signals = (const T*)signals;
+    P.out = out;
+    P.spectra = (cx<T>*)spectra;
+    P.N = (int)hp.N;
+    P.F = forward_only ? 0 : hp.F;
+    P.S = (int)S;
+    P.tsh = hp.tsh;
+    P.pitch = hp.pitch;
+    P.out_mode = output;
+    P.bl_mode = bl;
+    P.bl_lo = (int)blo;
+    P.bl_hi = (int)bhi;
+    P.st = hp.st;
+    P.tw = (const cx<T>*)pl->d_tw;
+    P.sp = make_spec<T>(pl);
+    const int TT = 1 << hp.tsh;
+    const int ngroups = forward_only ? 1 : (hp.F + TT - 1) / TT;
+    // enough CTAs to fill the machine a few times over when there are few signals
+    const long long target = 4LL * device_sms(hp.device);
+    long long fs = (target + S - 1) / S;
+    if (fs > ngroups) fs = ngroups;
+    if (fs < 1) fs = 1;
+    P.fsplit = (int)fs;
+    const long long grid = S * fs;
+    if (grid > 2147483647LL) return fail(NWCWT_ERR_INVALID, "too many signals for one launch");
+    { LaunchScope ls(0, stream); CUDA_TRY(launch_short<T>(P, (unsigned)grid, hp.nthr_short, hp.smem_short, stream)); }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static LongParams<T> make_long(nwcwt_plan* pl) {
+    const HostPlan& hp = pl->hp;
+    LongParams<T> P;
+    memset(&P, 0, sizeof(P));
+    P.N = hp.N;
+    P.N1 = hp.N1;
+    P.N2 = hp.N2;
+    P.tshA = hp.tshA;
+    P.pitchA = hp.pitchA;
+    P.tshB = hp.tshB;
+    P.stA = hp.stA;
+    P.stB = hp.stB;
+    P.twA = (const cx<T>*)pl->d_twA;
+    P.twB = (const cx<T>*)pl->d_twB;
+    P.twH = (const cx<T>*)pl->d_twH;
+    P.twL = (const cx<T>*)pl->d_twL;
+    P.lb = hp.lb;
+    P.tm_stride = hp.tm_stride;
+    P.sp = make_spec<T>(pl);
+    return P;
+}
+
+// workspace layout of the long path: [ring] spectra of N, then [ring] Tm slots
+template <typename T>
+static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spectra_out, long long S, int output,
+                       int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
+                       bool forward_only) {
+    const HostPlan& hp = pl->hp;
+    const size_t xbytes = align_up((size_t)hp.ring * hp.N * sizeof(cx<T>), 256);
+    const size_t tbytes = align_up((size_t)hp.ring * hp.tm_stride * sizeof(cx<T>), 256);
+    if (ws_bytes < xbytes + tbytes || !ws) return fail(NWCWT_ERR_WORKSPACE, "workspace too small");
+    cx<T>* X = (cx<T>*)ws;
+    cx<T>* Tm = (cx<T>*)((char*)ws + xbytes);
+    LongParams<T> P = make_long<T>(pl);
+    P.Tm = Tm;
+    const int TA = 1 << hp.tshA, TB = 1 << hp.tshB;
+    const unsigned tilesA = (unsigned)((hp.N2 + TA - 1) / TA), tilesB = (unsigned)((hp.N1 + TB - 1) / TB);
+    const size_t esz = (output == NWCWT_OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
+    for (long long s0 = 0; s0 < S; s0 += hp.ring) {
+        const int gs = (int)std::min<long long>(hp.ring, S - s0);
+        // forward transforms of gs signals (scipy.fftpack.fft, base.py:399)
+        P.signal = (const T*)signals + (size_t)s0 * hp.N;
+        P.Xout = forward_only ? (cx<T>*)spectra_out + (size_t)s0 * hp.N : X;
+        { LaunchScope ls(1, stream); CUDA_TRY(launch_passA<T>(-1, P, dim3(tilesA, gs), hp.nthr_long, hp.smem_A, stream)); }
+        { LaunchScope ls(2, stream); CUDA_TRY(launch_passB<T>(-1, P, dim3(tilesB, gs), hp.nthr_long, hp.smem_B, stream)); }
+        if (forward_only) continue;
+        for (int si = 0; si < gs; ++si) {
+            P.X = X + (size_t)si * hp.N;
+            char* out_s = (char*)out + (size_t)(s0 + si) * hp.F * (size_t)hp.N * esz;
+            for (int f0 = 0; f0 < hp.F; f0 += hp.ring) {
+                const int g = std::min(hp.ring, hp.F - f0);
+                P.f0 = f0;
+                P.out = out_s + (size_t)f0 * (size_t)hp.N * esz;
+                P.out_mode = output;
+                { LaunchScope ls(3, stream); CUDA_TRY(launch_passA<T>(1, P, dim3(tilesA, g), hp.nthr_long, hp.smem_A, stream)); }
+                { LaunchScope ls(4, stream); CUDA_TRY(launch_passB<T>(1, P, dim3(tilesB, g), hp.nthr_long, hp.smem_B, stream)); }
+            }
+            if (bl != NWCWT_BL_NONE) {
+                LaunchScope ls(5, stream);
+                nwcwt_baseline_rows_kernel<T><<<hp.F, 512, 0, stream>>>((T*)out_s, hp.N, bl, (int)blo, (int)bhi);
+            }
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int run_transform(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
+                         int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
+                         bool forward_only) {
+    if (pl->hp.path == 0)
+        return launch_short<T>(pl, signals, out, spectra, S, output, bl, blo, bhi, stream, forward_only);
+    return launch_long<T>(pl, signals, out, spectra, S, output, bl, blo, bhi, ws, ws_bytes, stream, forward_only);
+}
+
+static int check_args(const nwcwt_plan* pl, int output, int bl, long long& blo, long long& bhi) {
+    if (!pl) return fail(NWCWT_ERR_INVALID, "null plan");
+    if (output < NWCWT_OUT_CWT || output > NWCWT_OUT_POWER) return fail(NWCWT_ERR_INVALID, "bad output mode");
+    if (bl < NWCWT_BL_NONE || bl > NWCWT_BL_ZLOG) return fail(NWCWT_ERR_INVALID, "bad baseline mode");
+    if (bl != NWCWT_BL_NONE) {
+        if (output == NWCWT_OUT_CWT) return fail(NWCWT_ERR_INVALID, "baseline needs a real output (abs/power)");
+        // python slice semantics of wave[lo:hi] for non-negative indices (base.py:49)
+        if (blo < 0 || bhi < 0) return fail(NWCWT_ERR_INVALID, "negative baseline index");
+        if (bhi > pl->hp.N) bhi = pl->hp.N;
+        if (blo > bhi) blo = bhi;
+    }
+    if (pl->hp.F <= 0) return fail(NWCWT_ERR_INVALID, "plan has no frequencies");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+int nwcwt_version(void) { return NWCWT_VERSION; }
+int64_t nwcwt_launch_count(void) { return g_launches.load(); }
+
+int nwcwt_profile_enable(int32_t on) {
+    g_profile = on != 0;
+    return 0;
+}
+
+int nwcwt_profile_read(double ms[6], int64_t launches[6]) {
+    if (!ms || !launches) return fail(NWCWT_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (ProfEvent& e : g_prof_events) {
+        CUDA_TRY(cudaEventSynchronize(e.b));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, e.a, e.b));
+        g_prof_ms[e.cls] += t;
+        g_prof_n[e.cls] += 1;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof_events.clear();
+    for (int i = 0; i < 6; ++i) {
+        ms[i] = g_prof_ms[i];
+        launches[i] = g_prof_n[i];
+        g_prof_ms[i] = 0;
+        g_prof_n[i] = 0;
+    }
+    return 0;
+}
+const char* nwcwt_last_error(void) { return g_err.c_str(); }
+
+int nwcwt_plan_create(nwcwt_plan** out, const nwcwt_plan_desc* d) {
+    if (!out || !d) return fail(NWCWT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->dtype != NWCWT_F32 && d->dtype != NWCWT_F64) return fail(NWCWT_ERR_INVALID, "bad dtype");
+    if (d->family < NWCWT_MORSE || d->family > NWCWT_TABLE) return fail(NWCWT_ERR_INVALID, "bad family");
+    if (d->n < 2) return fail(NWCWT_ERR_INVALID, "signal length must be >= 2");
+    if (d->n >= (1LL << 31)) return fail(NWCWT_ERR_UNSUPPORTED, "signal length >= 2^31");
+    if (d->n_freqs < 0 || (d->n_freqs > 0 && !d->freqs)) return fail(NWCWT_ERR_INVALID, "bad freqs");
+    if (!(d->sfreq > 0)) return fail(NWCWT_ERR_INVALID, "sfreq must be positive");
+    for (int i = 0; i < d->n_freqs; ++i)
+        if (d->freqs[i] == 0) return fail(NWCWT_ERR_ZERO_FREQ, "freq == 0 (ZeroDivisionError, base.py:234-235)");
+    if (d->family == NWCWT_MORLET && d->n_freqs > 0 && !d->aux)
+        return fail(NWCWT_ERR_INVALID, "Morlet needs aux = peak_freq(freq)");
+    if (d->family == NWCWT_TABLE && (d->table_len < 1 || (d->n_freqs > 0 && !d->table)))
+        return fail(NWCWT_ERR_INVALID, "TABLE family needs table and table_len");
+    nwcwt_plan* pl = new nwcwt_plan();
+    HostPlan& hp = pl->hp;
+    hp.device = d->device;
+    hp.dtype = d->dtype;
+    hp.family = d->family;
+    hp.interpolate = d->interpolate ? 1 : 0;
+    hp.N = d->n;
+    hp.F = d->n_freqs;
+    hp.sfreq = d->sfreq;
+    hp.p0 = d->p0;
+    hp.p1 = d->p1;
+    hp.p2 = d->p2;
+    hp.prune_eps = d->prune_eps < 0 ? (d->dtype == NWCWT_F32 ? 1e-12 : 1e-24) : d->prune_eps;
+    hp.freqs.assign(d->freqs, d->freqs + d->n_freqs);
+    if (d->family == NWCWT_MORLET) hp.aux.assign(d->aux, d->aux + d->n_freqs);
+    if (d->family == NWCWT_TABLE) {
+        hp.table_len = d->table_len;
+        hp.table.assign(d->table, d->table + 2 * (size_t)d->n_freqs * (size_t)d->table_len);
+        if (d->table_lens) hp.table_lens.assign(d->table_lens, d->table_lens + d->n_freqs);
+    }
+    plan_geometry(hp);
+    plan_bands(hp);
+    std::string err;
+    if (!plan_shape(hp, err)) {
+        delete pl;
+        return fail(NWCWT_ERR_UNSUPPORTED, err);
+    }
+    *out = pl;
+    return 0;
+}
+
+int nwcwt_plan_destroy(nwcwt_plan* pl) {
+    if (!pl) return 0;
+    if (pl->on_device || pl->h_stream[0]) {
+        cudaSetDevice(pl->hp.device);
+        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table,
+                        pl->h_in_dev[0], pl->h_in_dev[1], pl->h_out_dev[0], pl->h_out_dev[1], pl->h_ws[0], pl->h_ws[1]};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+        for (int i = 0; i < 2; ++i)
+            if (pl->h_stream[i]) cudaStreamDestroy(pl->h_stream[i]);
+    }
+    delete pl;
+    return 0;
+}
+
+int nwcwt_plan_get_info(const nwcwt_plan* pl, nwcwt_plan_info* info) {
+    if (!pl || !info) return fail(NWCWT_ERR_INVALID, "null argument");
+    const HostPlan& hp = pl->hp;
+    memset(info, 0, sizeof(*info));
+    info->n = hp.N;
+    info->n_freqs = hp.F;
+    info->path = hp.path;
+    info->band_bins = hp.band_bins;
+    if (hp.path == 0) {
+        info->batch = 1 << hp.tsh;
+        info->n_stages[0] = hp.st.nst;
+        for (int i = 0; i < hp.st.nst; ++i) info->radices[0][i] = hp.st.radix[i];
+        info->smem_bytes = (int64_t)hp.smem_short;
+    } else {
+        info->n1 = hp.N1;
+        info->n2 = hp.N2;
+        info->batch = 1 << hp.tshA;
+        info->n_stages[0] = hp.stA.nst;
+        info->n_stages[1] = hp.stB.nst;
+        for (int i = 0; i < hp.stA.nst; ++i) info->radices[0][i] = hp.stA.radix[i];
+        for (int i = 0; i < hp.stB.nst; ++i) info->radices[1][i] = hp.stB.radix[i];
+        info->smem_bytes = (int64_t)std::max(hp.smem_A, hp.smem_B);
+    }
+    return 0;
+}
+
+int nwcwt_plan_get_bands(const nwcwt_plan* pl, int32_t* lo, int32_t* hi) {
+    if (!pl || !lo || !hi) return fail(NWCWT_ERR_INVALID, "null argument");
+    for (int i = 0; i < pl->hp.F; ++i) {
+        lo[i] = pl->hp.rec[i].lo;
+        hi[i] = pl->hp.rec[i].hi;
+    }
+    return 0;
+}
+
+int nwcwt_workspace_bytes(const nwcwt_plan* pl, int64_t n_signals, size_t* bytes) {
+    if (!pl || !bytes) return fail(NWCWT_ERR_INVALID, "null argument");
+    (void)n_signals;
+    const HostPlan& hp = pl->hp;
+    if (hp.path == 0) {
+        *bytes = 0;
+        return 0;
+    }
+    const size_t cs = cx_size(hp.dtype);
+    *bytes = align_up((size_t)hp.ring * hp.N * cs, 256) + align_up((size_t)hp.ring * hp.tm_stride * cs, 256);
+    return 0;
+}
+
+int nwcwt_spectrum_bank(nwcwt_plan* pl, void* bank, void* stream) {
+    if (!pl || !bank) return fail(NWCWT_ERR_INVALID, "null argument");
+    int rc = ensure_device(pl);
+    if (rc) return rc;
+    const HostPlan& hp = pl->hp;
+    if (hp.F <= 0) return 0;
+    dim3 grid((unsigned)((hp.N + 255) / 256), (unsigned)hp.F);
+    if (hp.dtype == NWCWT_F32) {
+        SpecParams<float> sp = make_spec<float>(pl);
+        sp.norm = 1.0f;
+        nwcwt_bank_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, (cx<float>*)bank, hp.F, hp.N);
+    } else {
+        SpecParams<double> sp = make_spec<double>(pl);
+        sp.norm = 1.0;
+        nwcwt_bank_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, (cx<double>*)bank, hp.F, hp.N);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int nwcwt_reduce_epochs(nwcwt_plan* pl, const void* in, void* out, int64_t E, int64_t count, int32_t kind,
+                        void* stream) {
+    if (!pl || !in || !out) return fail(NWCWT_ERR_INVALID, "null argument");
+    if (E <= 0 || count <= 0 || kind < 0 || kind > 1) return fail(NWCWT_ERR_INVALID, "bad reduction arguments");
+    CUDA_TRY(cudaSetDevice(pl->hp.device));
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (pl->hp.dtype == NWCWT_F32)
+        nwcwt_reduce_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(in, (float*)out, E, count, kind);
+    else
+        nwcwt_reduce_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(in, (double*)out, E, count, kind);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int nwcwt_baseline_rows(int32_t device, int32_t dtype, void* rows, int64_t n_rows, int64_t n, int32_t bl,
+                        int64_t blo, int64_t bhi, void* stream) {
+    if (!rows) return fail(NWCWT_ERR_INVALID, "null argument");
+    if (bl <= NWCWT_BL_NONE || bl > NWCWT_BL_ZLOG) return fail(NWCWT_ERR_INVALID, "bad baseline mode");
+    if (n_rows <= 0 || n <= 0) return 0;
+    if (n_rows > 2147483647LL) return fail(NWCWT_ERR_INVALID, "too many rows");
+    if (blo < 0 || bhi < 0) return fail(NWCWT_ERR_INVALID, "negative baseline index");
+    if (bhi > n) bhi = n;
+    if (blo > bhi) blo = bhi;
+    CUDA_TRY(cudaSetDevice(device));
+    if (dtype == NWCWT_F32)
+        nwcwt_baseline_rows_kernel<float><<<(unsigned)n_rows, 512, 0, (cudaStream_t)stream>>>((float*)rows, n, bl, (int)blo, (int)bhi);
+    else
+        nwcwt_baseline_rows_kernel<double><<<(unsigned)n_rows, 512, 0, (cudaStream_t)stream>>>((double*)rows, n, bl, (int)blo, (int)bhi);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int nwcwt_forward(nwcwt_plan* pl, const void* signals, void* spectra, int64_t S, void* ws, size_t ws_bytes,
+                  void* stream) {
+    if (!pl || !signals || !spectra) return fail(NWCWT_ERR_INVALID, "null argument");
+    if (S <= 0) return 0;
+    int rc = ensure_device(pl);
+    if (rc) return rc;
+    if (pl->hp.dtype == NWCWT_F32)
+        return run_transform<float>(pl, signals, nullptr, spectra, S, 0, 0, 0, 0, ws, ws_bytes, (cudaStream_t)stream, true);
+    return run_transform<double>(pl, signals, nullptr, spectra, S, 0, 0, 0, 0, ws, ws_bytes, (cudaStream_t)stream, true);
+}
+
+int nwcwt_transform(nwcwt_plan* pl, const void* signals, void* out, int64_t S, int32_t output, int32_t bl,
+                    int64_t blo, int64_t bhi, void* ws, size_t ws_bytes, void* stream) {
+    long long lo = blo, hi = bhi;
+    int rc = check_args(pl, output, bl, lo, hi);
+    if (rc) return rc;
+    if (!signals || !out) return fail(NWCWT_ERR_INVALID, "null buffer");
+    if (S <= 0) return 0;
+    if ((rc = ensure_device(pl))) return rc;
+    if (pl->hp.dtype == NWCWT_F32)
+        return run_transform<float>(pl, signals, out, nullptr, S, output, bl, lo, hi, ws, ws_bytes, (cudaStream_t)stream, false);
+    return run_transform<double>(pl, signals, out, nullptr, S, output, bl, lo, hi, ws, ws_bytes, (cudaStream_t)stream, false);
+}
+
+int nwcwt_transform_host(nwcwt_plan* pl, const void* signals, void* out, int64_t S, int32_t output, int32_t bl,
+                         int64_t blo, int64_t bhi) {
+    long long lo = blo, hi = bhi;
+    int rc = check_args(pl, output, bl, lo, hi);
+    if (rc) return rc;
+    if (!signals || !out) return fail(NWCWT_ERR_INVALID, "null buffer");
+    if (S <= 0) return 0;
+    if ((rc = ensure_device(pl))) return rc;
+    const HostPlan& hp = pl->hp;
+    const size_t rs = hp.dtype == NWCWT_F32 ? 4 : 8;
+    const size_t esz = output == NWCWT_OUT_CWT ? 2 * rs : rs;
+    const size_t in_row = (size_t)hp.N * rs, out_sig = (size_t)hp.F * (size_t)hp.N * esz;
+    // chunk: about 512 MB of output per slot, at least one signal
+    long long chunk = (long long)std::max<size_t>(1, ((size_t)512 << 20) / std::max<size_t>(out_sig, 1));
+    chunk = std::min<long long>(chunk, (S + 1) / 2 > 0 ? (S + 1) / 2 : 1);
+    if (chunk < 1) chunk = 1;
+    size_t wsb = 0;
+    nwcwt_workspace_bytes(pl, chunk, &wsb);
+    const size_t need_in = in_row * chunk, need_out = out_sig * chunk;
+    if (pl->h_in_bytes < need_in || pl->h_out_bytes < need_out || pl->h_ws_bytes < wsb || !pl->h_stream[0]) {
+        for (int i = 0; i < 2; ++i) {
+            if (pl->h_in_dev[i]) cudaFree(pl->h_in_dev[i]);
+            if (pl->h_out_dev[i]) cudaFree(pl->h_out_dev[i]);
+            if (pl->h_ws[i]) cudaFree(pl->h_ws[i]);
+            pl->h_in_dev[i] = pl->h_out_dev[i] = pl->h_ws[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&pl->h_in_dev[i], need_in));
+            CUDA_TRY(cudaMalloc(&pl->h_out_dev[i], need_out));
+            if (wsb) CUDA_TRY(cudaMalloc(&pl->h_ws[i], wsb));
+            if (!pl->h_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&pl->h_stream[i], cudaStreamNonBlocking));
+        }
+        pl->h_in_bytes = need_in;
+        pl->h_out_bytes = need_out;
+        pl->h_ws_bytes = wsb;
+    }
+    int slot = 0;
+    for (long long s0 = 0; s0 < S; s0 += chunk, slot ^= 1) {
+        const long long cs = std::min<long long>(chunk, S - s0);
+        cudaStream_t st = pl->h_stream[slot];
+        CUDA_TRY(cudaMemcpyAsync(pl->h_in_dev[slot], (const char*)signals + (size_t)s0 * in_row, in_row * cs,
+                                 cudaMemcpyHostToDevice, st));
+        if (hp.dtype == NWCWT_F32)
+            rc = run_transform<float>(pl, pl->h_in_dev[slot], pl->h_out_dev[slot], nullptr, cs, output, bl, lo, hi,
+                                      pl->h_ws[slot], wsb, st, false);
+        else
+            rc = run_transform<double>(pl, pl->h_in_dev[slot], pl->h_out_dev[slot], nullptr, cs, output, bl, lo, hi,
+                                       pl->h_ws[slot], wsb, st, false);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync((char*)out + (size_t)s0 * out_sig, pl->h_out_dev[slot], out_sig * cs,
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(pl->h_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(pl->h_stream[1]));
+    return 0;
+}
+
+}  // extern "C"

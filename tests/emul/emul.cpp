@@ -1,0 +1,126 @@
+// Host emulation of the kernel bodies (TEST INFRASTRUCTURE, never shipped, never
+// linked into libnwcwt.so).  The CUDA kernel bodies in ninwavelets_b200/csrc are
+// written against (block, tid, nthr, smem); here each block is stepped by a single
+// "thread" on the CPU so the index algebra, the radix plans, the band logic and the
+// epilogues can be checked against the oracle in the GPU-less authoring container.
+// It proves nothing about races or barriers - the GPU parity tests do that.
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nwcwt.h"
+#include "../../ninwavelets_b200/csrc/nw_common.h"
+#include "../../ninwavelets_b200/csrc/nw_fft.cuh"
+#include "../../ninwavelets_b200/csrc/nw_family.cuh"
+#include "../../ninwavelets_b200/csrc/nw_kernels.cuh"
+#include "../../ninwavelets_b200/csrc/nw_plan.h"
+
+using namespace nw;
+
+template <typename T>
+static void fill_tw(std::vector<cx<T>>& v, long long count, long long P, long long step) {
+    v.resize((size_t)count);
+    const long double tp = 6.283185307179586476925286766559005768L;
+    for (long long j = 0; j < count; ++j) {
+        const long long m = (j * step) % P;
+        const long double a = tp * (long double)m / (long double)P;
+        v[(size_t)j].x = (T)cosl(a);
+        v[(size_t)j].y = (T)sinl(a);
+    }
+}
+
+template <typename T>
+static int run(const HostPlan& hp, const void* signals, void* out, long long S, int output, int bl, long long blo,
+               long long bhi) {
+    std::vector<cx<T>> table;
+    if (hp.family == FAM_TABLE) {
+        table.resize((size_t)hp.F * hp.table_len);
+        for (size_t i = 0; i < table.size(); ++i) { table[i].x = (T)hp.table[2 * i]; table[i].y = (T)hp.table[2 * i + 1]; }
+    }
+    SpecParams<T> sp;
+    sp.family = hp.family; sp.grid_off = hp.grid_off; sp.df = hp.df; sp.p0 = hp.p0; sp.p1 = hp.p1;
+    sp.p2 = hp.family == FAM_MORSE ? hp.p0 / hp.p1 : hp.p2;
+    sp.norm = (T)(1.0 / (double)hp.N);
+    sp.rec = hp.rec.data(); sp.table = table.data(); sp.table_len = hp.table_len;
+    const size_t esz = output == OUT_CWT ? sizeof(cx<T>) : sizeof(T);
+    if (hp.path == 0) {
+        std::vector<cx<T>> tw;
+        fill_tw<T>(tw, hp.N, hp.N, 1);
+        ShortParams<T> P;
+        memset(&P, 0, sizeof(P));
+        P.signals = (const T*)signals; P.out = out; P.N = (int)hp.N; P.F = hp.F; P.S = (int)S;
+        P.tsh = hp.tsh; P.pitch = hp.pitch; P.out_mode = output; P.bl_mode = bl; P.bl_lo = (int)blo; P.bl_hi = (int)bhi;
+        P.st = hp.st; P.tw = tw.data(); P.sp = sp;
+        const int TT = 1 << hp.tsh, ngroups = (hp.F + TT - 1) / TT;
+        P.fsplit = ngroups < 3 ? ngroups : 3;
+        std::vector<char> smem(hp.smem_short + 64);
+        for (long long b = 0; b < S * P.fsplit; ++b) short_body<T>(P, smem.data(), (int)b, 0, 1);
+        return 0;
+    }
+    std::vector<cx<T>> twA, twB, twH, twL;
+    fill_tw<T>(twA, hp.N1, hp.N1, 1);
+    fill_tw<T>(twB, hp.N2, hp.N2, 1);
+    const long long nL = 1LL << hp.lb, nH = (hp.N + nL - 1) / nL;
+    fill_tw<T>(twL, nL, hp.N, 1);
+    fill_tw<T>(twH, nH, hp.N, nL);
+    LongParams<T> P;
+    memset(&P, 0, sizeof(P));
+    P.N = hp.N; P.N1 = hp.N1; P.N2 = hp.N2; P.tshA = hp.tshA; P.pitchA = hp.pitchA; P.tshB = hp.tshB;
+    P.stA = hp.stA; P.stB = hp.stB; P.twA = twA.data(); P.twB = twB.data(); P.twH = twH.data(); P.twL = twL.data();
+    P.lb = hp.lb; P.tm_stride = hp.tm_stride; P.sp = sp;
+    const int ring = hp.ring < 3 ? hp.ring : 3;
+    std::vector<cx<T>> X((size_t)ring * hp.N), Tm((size_t)ring * hp.tm_stride);
+    P.Tm = Tm.data();
+    const int TA = 1 << hp.tshA, TB = 1 << hp.tshB;
+    const int tilesA = (hp.N2 + TA - 1) / TA, tilesB = (hp.N1 + TB - 1) / TB;
+    std::vector<char> smem(std::max(hp.smem_A, hp.smem_B) + 64);
+    for (long long s0 = 0; s0 < S; s0 += ring) {
+        const int gs = (int)std::min<long long>(ring, S - s0);
+        P.signal = (const T*)signals + (size_t)s0 * hp.N;
+        P.Xout = X.data();
+        for (int y = 0; y < gs; ++y) for (int x = 0; x < tilesA; ++x) passA_body<T, -1>(P, smem.data(), x, y, 0, 1);
+        for (int y = 0; y < gs; ++y) for (int x = 0; x < tilesB; ++x) passB_body<T, -1>(P, smem.data(), x, y, 0, 1);
+        for (int si = 0; si < gs; ++si) {
+            P.X = X.data() + (size_t)si * hp.N;
+            char* out_s = (char*)out + (size_t)(s0 + si) * hp.F * (size_t)hp.N * esz;
+            for (int f0 = 0; f0 < hp.F; f0 += ring) {
+                const int g = std::min(ring, hp.F - f0);
+                P.f0 = f0; P.out = out_s + (size_t)f0 * hp.N * esz; P.out_mode = output;
+                for (int y = 0; y < g; ++y) for (int x = 0; x < tilesA; ++x) passA_body<T, 1>(P, smem.data(), x, y, 0, 1);
+                for (int y = 0; y < g; ++y) for (int x = 0; x < tilesB; ++x) passB_body<T, 1>(P, smem.data(), x, y, 0, 1);
+            }
+            if (bl != BL_NONE) {
+                double sh[2];
+                for (int f = 0; f < hp.F; ++f) baseline_rows_body<T>((T*)out_s, hp.N, bl, (int)blo, (int)bhi, sh, f, 0, 1);
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int emul_transform(const nwcwt_plan_desc* d, const void* signals, void* out, long long S, int output,
+                              int bl, long long blo, long long bhi, int force_long, char* errbuf, int errlen) {
+    HostPlan hp;
+    hp.device = 0; hp.dtype = d->dtype; hp.family = d->family; hp.interpolate = d->interpolate ? 1 : 0;
+    hp.N = d->n; hp.F = d->n_freqs; hp.sfreq = d->sfreq; hp.p0 = d->p0; hp.p1 = d->p1; hp.p2 = d->p2;
+    hp.prune_eps = d->prune_eps < 0 ? (d->dtype == 0 ? 1e-12 : 1e-24) : d->prune_eps;
+    hp.freqs.assign(d->freqs, d->freqs + d->n_freqs);
+    if (d->family == FAM_MORLET) hp.aux.assign(d->aux, d->aux + d->n_freqs);
+    if (d->family == FAM_TABLE) {
+        hp.table_len = d->table_len;
+        hp.table.assign(d->table, d->table + 2 * (size_t)d->n_freqs * (size_t)d->table_len);
+        if (d->table_lens) hp.table_lens.assign(d->table_lens, d->table_lens + d->n_freqs);
+    }
+    plan_geometry(hp);
+    plan_bands(hp);
+    std::string err;
+    if (!plan_shape(hp, err, force_long != 0)) {
+        strncpy(errbuf, err.c_str(), errlen - 1);
+        return -2;
+    }
+    if (bhi > hp.N) bhi = hp.N;
+    if (blo > bhi) blo = bhi;
+    return d->dtype == 0 ? run<float>(hp, signals, out, S, output, bl, blo, bhi)
+                         : run<double>(hp, signals, out, S, output, bl, blo, bhi);
+}

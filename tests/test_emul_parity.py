@@ -1,0 +1,102 @@
+"""CPU check of the CUDA kernel bodies (host emulation, tests/emul) against the golden fixtures.
+
+This does NOT replace the GPU parity tests: it validates the arithmetic and index algebra of
+the exact code the kernels run (same headers), sequentially, so that GPU time is not spent on
+logic errors.  Tolerances are the BASELINE.json ones: fp64 max|out-ref|/max|ref| per row <=
+1e-12, fp32 per-row relative L2 <= 1e-5 against the fp64 reference on the float32-rounded input.
+"""
+import numpy as np
+import pytest
+
+import cwt_oracle as orc
+from emul_util import desc_from_oracle_family, emul_transform
+from golden_util import case_wave, l2_rel_err, peak_rel_err
+
+F64_TOL = 1e-12
+F32_TOL = 1e-5
+
+SMALL = ["readme_morse", "readme_morlet", "morse_n300", "morse_n301", "morlet_n1000", "gabor_n1500", "morse_b3_n1500",
+         "morlet_s5_n300", "shannon_n1500", "mexicanhat_n1500", "mexicanhat_n301", "haar_n1000", "morse_n4096",
+         "morse_interp_n301", "morlet_interp_n1500", "shannon_interp_n300", "mexicanhat_interp_n300",
+         "morse_fractional", "morse_beyond_nyquist", "morlet_beyond_nyquist", "morse_sfreq256", "mexicanhat_rwl2"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_emul_fp64_matches_reference(golden_transforms, name):
+    c = golden_transforms[name]
+    fam = orc.Family(c["kind"], **c["kw"])
+    x = case_wave(c)
+    d = desc_from_oracle_family(fam, c["freqs"], len(x), dtype=1)
+    z = emul_transform(d, x[None, :], output=0)[0]
+    assert peak_rel_err(z, c["cwt"]).max() <= F64_TOL, name
+    p = emul_transform(d, x[None, :], output=2)[0]
+    assert peak_rel_err(p, np.abs(c["cwt"]) ** 2).max() <= F64_TOL, name
+
+
+@pytest.mark.parametrize("name", ["readme_morse", "morse_n1500", "morlet_n1500", "shannon_n1000", "mexicanhat_n1500",
+                                  "morse_interp_n300", "morse_n4096"])
+def test_emul_fp32_matches_reference(golden_transforms, name):
+    c = golden_transforms[name]
+    fam = orc.Family(c["kind"], **c["kw"])
+    x32 = case_wave(c).astype(np.float32)
+    ref = orc.cwt(fam, x32.astype(np.float64), c["freqs"])
+    d = desc_from_oracle_family(fam, c["freqs"], len(x32), dtype=0)
+    z = emul_transform(d, x32[None, :], output=0)[0]
+    err = l2_rel_err(z.astype(np.complex128), ref)
+    assert (err <= F32_TOL).all(), (name, err)
+
+
+@pytest.mark.parametrize("name,dtype", [("morse_n1500", 1), ("morlet_n1000", 1), ("mexicanhat_n1500", 1),
+                                        ("morse_n4096", 0), ("shannon_n1500", 1), ("morse_interp_n301", 1)])
+def test_emul_long_path_forced(golden_transforms, name, dtype):
+    """The two-pass (four-step) kernels on sizes small enough to emulate."""
+    c = golden_transforms[name]
+    fam = orc.Family(c["kind"], **c["kw"])
+    x = case_wave(c)
+    if dtype == 0:
+        x = x.astype(np.float32)
+    ref = orc.cwt(fam, x.astype(np.float64), c["freqs"])
+    d = desc_from_oracle_family(fam, c["freqs"], len(x), dtype=dtype)
+    z = emul_transform(d, x[None, :], output=0, force_long=True)[0]
+    if dtype == 1:
+        assert peak_rel_err(z, ref).max() <= F64_TOL
+    else:
+        assert l2_rel_err(z.astype(np.complex128), ref).max() <= F32_TOL
+
+
+def test_emul_long_65536(golden_transforms):
+    c = golden_transforms["morse_long_n65536"]
+    fam = orc.Family(c["kind"], **c["kw"])
+    x = case_wave(c)
+    d = desc_from_oracle_family(fam, c["freqs"], len(x), dtype=1)
+    z = emul_transform(d, x[None, :], output=0)[0]
+    assert peak_rel_err(z[:, c["cols"]], c["cwt"]).max() <= F64_TOL
+    p = np.abs(z) ** 2
+    np.testing.assert_allclose(p.sum(axis=1), c["row_power_sum"], rtol=1e-11)
+
+
+def test_emul_baseline_and_batch():
+    z = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "epochs.npz"))
+    fam = orc.Family("morlet", sfreq=1000.0, sigma=7.0)
+    x = z["data"][:, 1, :]
+    d = desc_from_oracle_family(fam, z["freqs"], x.shape[1], dtype=1)
+    out = emul_transform(d, x, output=2, baseline=5, lo=0, hi=200)
+    assert peak_rel_err(out, z["zscore_power"]).max() <= 1e-11
+    zc = emul_transform(d, x, output=0)
+    assert peak_rel_err(zc, z["cwt"]).max() <= F64_TOL
+    for mode, code in (("mean", 1), ("ratio", 2), ("percent", 3), ("log", 4), ("zlog", 6)):
+        ref = orc.baseline_rows(np.abs(z["cwt"][:2]) ** 2, 1000.0, 0.1, 0.3, mode)
+        got = emul_transform(d, x[:2], output=2, baseline=code, lo=100, hi=300)
+        assert peak_rel_err(got, ref).max() <= 1e-11, mode
+
+
+def test_emul_odd_lengths_and_generic_radix():
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 7, 77, 91, 143, 1001, 1331, 2 * 3 * 5 * 7 * 11):
+        x = rng.standard_normal(n)
+        fr = np.array([3.0, 20.0, 110.0])
+        fam = orc.Family("morse", sfreq=1000.0)
+        ref = orc.cwt(fam, x, fr)
+        d = desc_from_oracle_family(fam, fr, n, dtype=1)
+        z = emul_transform(d, x[None, :], output=0)[0]
+        assert peak_rel_err(z, ref).max() <= F64_TOL, n

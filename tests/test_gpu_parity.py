@@ -1,0 +1,237 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the public
+host mirror (ninwavelets_b200.Morse/...) and therefore through the C ABI of libnwcwt.so; the oracle
+and the golden fixtures (produced by the unmodified reference) are only the checker.
+
+Tolerances (BASELINE.json): fp64 max|out-ref|/max|ref| per row <= 1e-12; fp32 per-row relative L2
+<= 1e-5 against the fp64 reference evaluated on the float32-rounded input (metrics and their
+noise-floor clause: tests/golden_util.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import cwt_oracle as orc
+from golden_util import case_wave, l2_rel_err, peak_rel_err
+
+pytestmark = pytest.mark.gpu
+
+F64_TOL = 1e-12
+F32_TOL = 1e-5
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def nw():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import ninwavelets_b200 as pkg
+    return pkg
+
+
+def make(nw, kind, kw, **extra):
+    kw = dict(kw)
+    kw.update(extra)
+    ctor = {"morse": nw.Morse, "morlet": nw.Morlet, "shannon": nw.Shannon, "mexicanhat": nw.MexicanHat,
+            "haar": nw.Haar}[kind]
+    return ctor(cuda=True, **kw)
+
+
+def test_all_small_golden_cases_fp64(nw, golden_transforms):
+    worst = 0.0
+    n = 0
+    for name, c in golden_transforms.items():
+        if "cols" in c:
+            continue
+        x = case_wave(c)
+        obj = make(nw, c["kind"], c["kw"])
+        z = obj.cwt(x, c["freqs"])
+        assert z.shape == c["cwt"].shape and z.dtype == np.complex128, name
+        e = peak_rel_err(z, c["cwt"]).max()
+        worst = max(worst, e)
+        assert e <= F64_TOL, (name, e)
+        p = obj.power(x)                       # cached plan, freqs=None like the reference allows
+        assert peak_rel_err(p, np.abs(c["cwt"]) ** 2).max() <= F64_TOL, name
+        a = obj.abs(x)
+        assert peak_rel_err(a, np.abs(c["cwt"])).max() <= F64_TOL, name
+        n += 1
+    assert n >= 50
+    print("worst fp64 error over %d golden cases: %.3e" % (n, worst))
+
+
+def test_all_small_golden_cases_fp32(nw, golden_transforms):
+    worst = 0.0
+    for name, c in golden_transforms.items():
+        if "cols" in c:
+            continue
+        x32 = case_wave(c).astype(np.float32)
+        ref = orc.cwt(orc.Family(c["kind"], **c["kw"]), x32.astype(np.float64), c["freqs"])
+        z = make(nw, c["kind"], c["kw"], dtype="float32").cwt(x32, c["freqs"])
+        assert z.dtype == np.complex64
+        e = l2_rel_err(z.astype(np.complex128), ref).max()
+        worst = max(worst, e)
+        assert e <= F32_TOL, (name, e)
+    print("worst fp32 error: %.3e" % worst)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_long_rows_vs_golden_samples(nw, golden_transforms, dtype):
+    for name, c in golden_transforms.items():
+        if "cols" not in c:
+            continue
+        x = case_wave(c)
+        obj = make(nw, c["kind"], c["kw"], dtype=dtype)
+        if dtype == "float64":
+            z = obj.cwt(x, c["freqs"])
+            assert peak_rel_err(z[:, c["cols"]], c["cwt"]).max() <= F64_TOL, name
+            p = obj.power(x)
+            np.testing.assert_allclose(p.sum(axis=1), c["row_power_sum"], rtol=1e-11, err_msg=name)
+            np.testing.assert_allclose(p.max(axis=1), c["row_power_max"], rtol=1e-11, err_msg=name)
+        else:
+            # fp32: the golden is for the fp64 input; rounding the input adds ~6e-8 relative, far inside 1e-5
+            z = obj.cwt(x.astype(np.float32), c["freqs"]).astype(np.complex128)
+            assert l2_rel_err(z[:, c["cols"]], c["cwt"]).max() <= F32_TOL, name
+
+
+def test_spectrum_generator_vs_reference_spectra(nw):
+    """The in-register spectrum generator alone (nwcwt_spectrum_bank) against make_fft_wavelets of the
+    reference (golden spectra.npz, N = 1500)."""
+    z = np.load(os.path.join(GOLDEN, "spectra.npz"))
+    kws = {"morse": ("morse", dict(sfreq=1000, b=17.5, r=3)), "morlet": ("morlet", dict(sfreq=1000, sigma=7.)),
+           "gabor": ("morlet", dict(sfreq=1000, sigma=7., gabor=True)), "shannon": ("shannon", dict(sfreq=1000)),
+           "mexicanhat": ("mexicanhat", dict(sfreq=1000)), "haar": ("haar", dict(sfreq=1000))}
+    fr = [1., 2.5, 10., 99., 400.]
+    for name, (kind, kw) in kws.items():
+        for interp in (0, 1):
+            if kind == "haar" and interp:
+                continue
+            obj = make(nw, kind, kw, interpolate=bool(interp), prune_eps=0.0)
+            bank = obj.make_fft_wavelets(fr, 1.5)
+            for i in range(len(fr)):
+                ref = orc.pad_to(z["%s_%d_%d" % (name, interp, i)], 1500)
+                if interp:
+                    ref = orc.interpolate_alias(ref)
+                got = np.asarray(bank[i])
+                scale = max(np.abs(ref).max(), 1e-300)
+                assert np.abs(got - ref).max() / scale <= 1e-13, (name, interp, i)
+
+
+def test_baseline_modes_and_epochs(nw):
+    z = np.load(os.path.join(GOLDEN, "baseline.npz"))
+    w = z["wave"]
+    for mode in orc.BASELINE_MODES:
+        got = getattr(nw.Baseline(w, 1000, 0.0, 0.2), mode)()
+        np.testing.assert_allclose(got, z[mode], rtol=1e-13, atol=1e-14, err_msg=mode)
+    np.testing.assert_allclose(nw.Baseline(w, 1000, 0.1, 0.35).zscore(), z["zscore_100_350"], rtol=1e-13, atol=1e-14)
+
+    e = np.load(os.path.join(GOLDEN, "epochs.npz"))
+
+    class FakeEpochs:
+        info = {"sfreq": 1000.0}
+        ch_names = ["MEG0", "MEG1"]
+
+        def get_data(self):
+            return e["data"]
+
+    ew = nw.EpochsWavelet(FakeEpochs(), nw.Morlet(500, 7., cuda=True))   # sfreq is overwritten (mneutils.py:24)
+    assert ew.wavelet.sfreq == 1000.0
+    assert peak_rel_err(ew.cwt("MEG1", e["freqs"]), e["cwt"]).max() <= F64_TOL
+    assert peak_rel_err(ew.power("MEG1", e["freqs"]), e["power"]).max() <= F64_TOL
+    assert np.abs(ew.itc("MEG1", e["freqs"]) - e["itc"]).max() <= 1e-9
+    # cfg3: z-scored power rows, fused epilogue
+    m = nw.Morlet(1000, 7., cuda=True)
+    zs = m.power(e["data"][:, 1, :], e["freqs"], baseline=("zscore", 0.0, 0.2))
+    assert peak_rel_err(zs, e["zscore_power"]).max() <= 1e-10
+    zs32 = nw.Morlet(1000, 7., cuda=True, dtype="float32").power(e["data"][:, 1, :].astype(np.float32), e["freqs"],
+                                                                 baseline=("zscore", 0.0, 0.2))
+    assert l2_rel_err(zs32, e["zscore_power"]).max() <= 1e-4   # z-score amplifies by mean/std of the window
+
+
+def test_api_quirks_and_extensions(nw):
+    import torch
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((5, 1000))
+    m = nw.Morse(1000, cuda=True)
+    batch = m.power(x, np.arange(1, 41.0))
+    assert batch.shape == (5, 40, 1000)
+    for i in range(5):   # batched [S, N] input is bit-identical to the reference-style 1-D calls
+        assert np.array_equal(nw.Morse(1000, cuda=True).power(x[i], np.arange(1, 41.0)), batch[i])
+    # reuse=True ignores new freqs (reference base.py:394-395)
+    again = m.power(x[0], np.arange(50, 60.0))
+    assert np.array_equal(again, batch[0])
+    fresh = m.power(x[0], np.arange(50, 60.0), reuse=False)
+    assert fresh.shape == (10, 1000)
+    # a cached bank of another length is pad_to'ed onto the new signal (base.py:396-397)
+    fam = orc.Family("morse")
+    bank = orc.make_fft_wavelets(fam, np.arange(50, 60.0), 1.0)
+    ref = orc.cwt(fam, x[1][:700], None, bank=bank)
+    got = m.cwt(x[1][:700], None)
+    assert peak_rel_err(got, ref).max() <= F64_TOL
+    # torch CUDA tensor in -> tensor out, same numbers as the host path
+    xt = torch.as_tensor(x, device="cuda")
+    m2 = nw.Morse(1000, cuda=True)
+    pt = m2.power(xt, np.arange(1, 41.0))
+    assert pt.is_cuda and np.array_equal(pt.cpu().numpy(), batch)
+    # pruning off vs default
+    full = nw.Morse(1000, cuda=True, prune_eps=0.0).power(x, np.arange(1, 41.0))
+    assert peak_rel_err(full, batch).max() <= 1e-14
+    with pytest.raises(ZeroDivisionError):
+        nw.Morse(1000, cuda=True).cwt(x[0], [0.0, 1.0])
+    with pytest.raises(RuntimeError):
+        nw.Morse(1000).cwt(x[0], [1.0, 2.0])     # cuda=False: no CPU path in this package
+
+
+def test_user_subclass_plugin(nw):
+    """README.md:342-355 plugin API: a numpy trans_formula in a user subclass is tabulated and uploaded."""
+    class Bump(nw.WaveletBase):
+        def __init__(self, sfreq=1000, **kw):
+            super().__init__(sfreq, 1., False, True, **kw)
+            self.mode = nw.WaveletMode.Reverse
+
+        def trans_formula(self, freqs, freq=1.):
+            return np.exp(-np.square((freqs - freq) / (0.2 * freq)))
+
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(1200)
+    fr = np.array([5.0, 20.0, 80.0])
+    grid = np.arange(0, 1000 / 1.2 * 1.2, 1 / 1.2)
+    bank = np.array([orc.pad_to(np.exp(-np.square((grid - f) / (0.2 * f))), 1200) for f in fr])
+    from scipy.fftpack import fft, ifft
+    ref = ifft(bank * fft(x))
+    assert peak_rel_err(Bump().cwt(x, fr), ref).max() <= F64_TOL
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-5)])
+def test_properties_at_full_size(nw, dtype, tol):
+    """Size-independent checks at a BASELINE.json config-2 row size (N = 600 000)."""
+    n = 600000
+    t = np.arange(n) / 1000.0
+    fr = np.array([10.0, 40.0, 100.0])
+    m = make(nw, "morse", dict(sfreq=1000), dtype=dtype)
+    # (1) unit sinusoid at the analysis frequency has Morse power 1 (peak of the spectrum is exactly 2)
+    p = m.power(np.sin(2 * np.pi * 40.0 * t), fr)
+    assert abs(np.median(p[1]) - 1.0) <= 50 * tol and p[0].max() < 1e-6
+    # (2) linearity in the signal
+    rng = np.random.default_rng(4)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    za, zb, zab = m.cwt(a, None), m.cwt(b, None), m.cwt(a + 2 * b, None)
+    assert l2_rel_err(zab.astype(np.complex128), (za + 2 * zb).astype(np.complex128)).max() <= 20 * tol
+    # (3) Parseval: sum_n |z|^2 = (1/N) sum_k |W X|^2
+    X = np.fft.fft(a)
+    k = np.arange(n) * (1 / (n / 1000.0))
+    for i, f in enumerate(fr):
+        W = orc.analytic_spectrum(orc.Family("morse"), k, f)
+        lhs = (np.abs(za[i].astype(np.complex128)) ** 2).sum()
+        rhs = (np.abs(W * X) ** 2).sum() / n
+        assert abs(lhs - rhs) / rhs <= 100 * tol
+
+
+def test_forward_fft_entry_point(nw):
+    import torch
+    from ninwavelets_b200 import _backend as be
+    rng = np.random.default_rng(0)
+    for n in (300, 1001, 4096, 65536, 600000):
+        x = rng.standard_normal((2, n))
+        plan = be.Plan(device=0, dtype=np.float64, family=be.SHANNON, interpolate=False, n=n, sfreq=1000.0, freqs=[])
+        X = plan.forward_device(torch.as_tensor(x, device="cuda")).cpu().numpy()
+        ref = np.fft.fft(x, axis=1)
+        assert np.abs(X - ref).max() / np.abs(ref).max() <= 1e-14, n
