@@ -93,13 +93,17 @@ typedef struct nwcwt_plan nwcwt_plan;
 typedef struct nwcwt_plan_info {
     int64_t n;
     int32_t n_freqs;
-    int32_t path;          /* 0 = short rows (one CTA per signal), 1 = long rows (two passes) */
+    int32_t path;          /* 0 = short rows (one CTA per signal), 1 = long rows (two passes, generic
+                              kernels), 2 = long rows (two passes, packed in-place kernels) */
     int32_t n1, n2;        /* long rows: n = n1 * n2 */
     int32_t batch;         /* frequencies (short) / columns (long) interleaved per CTA */
     int32_t n_stages[2];   /* radix stages of the n (short) or n1, n2 (long) point transforms */
     int32_t radices[2][16];
     int64_t band_bins;     /* sum over frequencies of non-pruned bins */
     int64_t smem_bytes;    /* dynamic shared memory of the dominant kernel */
+    int32_t threads[2];    /* threads per CTA: short kernel / pass A, pass B */
+    int32_t rows_per_launch; /* long rows: (signal, frequency) rows per pass-A / pass-B launch pair */
+    int32_t reserved;
 } nwcwt_plan_info;
 
 int nwcwt_version(void);
@@ -111,6 +115,9 @@ int64_t nwcwt_launch_count(void);
  * accumulated milliseconds and launch counts of [0] short fused kernel, [1] forward pass A, [2] forward
  * pass B, [3] inverse pass A, [4] inverse pass B, [5] baseline rows, and resets them. */
 int nwcwt_profile_enable(int32_t on);
+/* Test hook: non-zero makes every transform use the generic (any-length) kernels even where the plan has
+ * the packed fast path, so both can be checked against the oracle on the same input. */
+int nwcwt_debug_force_generic(int32_t on);
 int nwcwt_profile_read(double ms[6], int64_t launches[6]);
 
 /* Host-side planning only (no CUDA call): factorisation, bands, tables.  Device

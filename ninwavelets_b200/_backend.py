@@ -40,6 +40,7 @@ class PlanInfo(C.Structure):
         ("n", C.c_int64), ("n_freqs", C.c_int32), ("path", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32),
         ("batch", C.c_int32), ("n_stages", C.c_int32 * 2), ("radices", (C.c_int32 * 16) * 2),
         ("band_bins", C.c_int64), ("smem_bytes", C.c_int64),
+        ("threads", C.c_int32 * 2), ("rows_per_launch", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -57,7 +58,7 @@ SYMBOLS = (
     "nwcwt_version", "nwcwt_last_error", "nwcwt_plan_create", "nwcwt_plan_destroy", "nwcwt_plan_get_info",
     "nwcwt_plan_get_bands", "nwcwt_workspace_bytes", "nwcwt_spectrum_bank", "nwcwt_reduce_epochs",
     "nwcwt_baseline_rows", "nwcwt_launch_count", "nwcwt_profile_enable", "nwcwt_profile_read",
-    "nwcwt_forward", "nwcwt_transform", "nwcwt_transform_host",
+    "nwcwt_forward", "nwcwt_transform", "nwcwt_transform_host", "nwcwt_debug_force_generic",
 )
 
 
@@ -107,6 +108,11 @@ def launch_count():
 
 
 PROFILE_CLASSES = ("short_fused", "fwd_passA", "fwd_passB", "inv_passA", "inv_passB", "baseline_rows")
+
+
+def force_generic(on):
+    """Test hook: run the generic kernels even where the plan has the packed fast path."""
+    _check(lib().nwcwt_debug_force_generic(C.c_int32(1 if on else 0)))
 
 
 def profile_enable(on):
@@ -166,8 +172,9 @@ class Plan:
     def info(self):
         i = PlanInfo()
         _check(lib().nwcwt_plan_get_info(self._h, C.byref(i)))
-        out = dict(n=i.n, n_freqs=i.n_freqs, path="short" if i.path == 0 else "long", n1=i.n1, n2=i.n2,
-                   batch=i.batch, band_bins=i.band_bins, smem_bytes=i.smem_bytes)
+        out = dict(n=i.n, n_freqs=i.n_freqs, path=("short", "long", "long_packed")[i.path], n1=i.n1, n2=i.n2,
+                   batch=i.batch, band_bins=i.band_bins, smem_bytes=i.smem_bytes, threads=list(i.threads),
+                   rows_per_launch=i.rows_per_launch)
         out["radices"] = [list(i.radices[k][: i.n_stages[k]]) for k in range(2)]
         return out
 

@@ -12,7 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnwcwt.so")
 SOURCES = ["nwcwt.cu", "k_short_f32.cu", "k_short_f64.cu", "k_passA_f32.cu", "k_passA_f64.cu",
-           "k_passB_f32.cu", "k_passB_f64.cu"]
+           "k_passB_f32.cu", "k_passB_f64.cu", "k_long2_f32_c0.cu", "k_long2_f32_c1.cu", "k_long2_f32_c2.cu",
+           "k_long2_f32_c3.cu", "k_long2_f64.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 
@@ -33,6 +34,8 @@ def _compile(src, verbose):
     r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stdout))
+    if "warning" in r.stdout:   # e.g. #20013-D (host constexpr called from device code) silently miscompiles
+        sys.stderr.write("nvcc warnings in %s:\n%s\n" % (src, r.stdout))
     return obj, r.stdout
 
 

@@ -20,7 +20,16 @@
 #define NW_SYNC() __syncthreads()
 #define NW_RESTRICT __restrict__
 #else
-#define NW_SYNC() ((void)0)
+// host instantiation (tests/emul): a barrier is a hook the emulator sets when it steps the
+// threads of a block as fibers; with one stepping thread it is a no-op
+namespace nw {
+typedef void (*host_sync_fn)();
+inline host_sync_fn& host_sync_hook() {
+    static host_sync_fn f = nullptr;
+    return f;
+}
+}  // namespace nw
+#define NW_SYNC() do { if (nw::host_sync_hook()) nw::host_sync_hook()(); } while (0)
 #define NW_RESTRICT
 #endif
 
@@ -83,6 +92,18 @@ struct FftStages {
     int ns[MAX_STAGES];
     fastdiv div_ns[MAX_STAGES];   // b / ns
     fastdiv div_pr[MAX_STAGES];   // lin / (P / radix)   (b-fastest mapping)
+};
+
+// Radix plan of the packed in-place engine (nw_fft2.cuh).  ns[s] = product of the radices before
+// stage s; stage s works in blocks of L_s = P / ns[s] with Q_s = L_s / radix[s] butterflies each.
+static const int MAX_STAGES2 = 8;
+struct Fft2Plan {
+    int P;
+    int nst;
+    int radix[MAX_STAGES2];
+    int ns[MAX_STAGES2];
+    fastdiv div_q[MAX_STAGES2];   // bi / Q_s
+    fastdiv div_r[MAX_STAGES2];   // x / radix[s]
 };
 
 }  // namespace nw

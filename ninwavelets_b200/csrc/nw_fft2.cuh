@@ -1,0 +1,237 @@
+// In-place, packed, mixed-radix shared-memory FFT engine (the fast path).
+//
+// A CTA transforms TT = 2*TP interleaved length-P sequences that live in ONE
+// shared-memory buffer buf[p * TP + tp] of two-lane complex values (cx2: lanes
+// = sequences 2*tp and 2*tp+1).  Every stage is an in-place Cooley-Tukey pass:
+// a butterfly reads and writes the same R slots, so there is no ping-pong
+// buffer and one barrier per stage; a thread takes as many butterflies as the
+// loop gives it, so any thread count works.
+//
+//   fft2_dif   natural-order input, digit-reversed output (decimation in frequency)
+//              stage s works in blocks of L_s = P / (R_0..R_{s-1}) with stride
+//              L_s / R_s and multiplies output r by w_{L_s}^{n' r}.  The last
+//              stage hands result index  rev(blk) + (P / R_last) * r  to Dst.
+//   fft2_dit   digit-reversed input (gathered through Src by the first pass, which
+//              runs the LAST radix), natural-order output: the transposed network.
+//
+// Twiddles: one table load per butterfly (w_{L_s}^{n'}), the other R-2 powers are
+// formed in registers - shared-memory / L1 bandwidth, not arithmetic, is the scarce
+// resource of these kernels ("what bounds the kernels").
+//
+// Src / Dst see a whole butterfly at a time so that they can hoist index arithmetic and run
+// recurrences over r:   src.load_all<R>(base, step, tp, v)   fills v[r] with element base + r*step of
+// sequences 2*tp, 2*tp+1;   ctx = dst.begin(base, step, tp)  is called before the butterfly's loads (so
+// the epilogue can start its own table loads) and   dst.store_all<R>(ctx, v)   receives results
+// base + r*step.
+//
+// DIR = +1: e^{+2 pi i n k / P} (inverse, unnormalised); DIR = -1: forward.
+// tw[j] = e^{+2 pi i j / P}, j in [0, P).
+#pragma once
+#include "nw_common.h"
+#include "nw_pk.cuh"
+#include "nw_bfly2.cuh"
+
+namespace nw {
+
+static const int MAX_PACKED_RADIX = 16;
+
+// digit reversal of a butterfly block index for the last DIF / first DIT pass:
+// blk = ((k_0 R_1 + k_1) R_2 + ...) over radices 0..m-2  ->  k_0 + R_0 k_1 + R_0 R_1 k_2 + ...
+NW_HD int fft2_rev(const Fft2Plan& st, int blk) {
+    int rev = 0;
+    // peel digits from the least significant (radix m-2) upwards
+    for (int s = st.nst - 2; s >= 0; --s) {
+        const int q = (int)fd_div((uint32_t)blk, st.div_r[s]);
+        const int d = blk - q * st.radix[s];
+        rev += d * st.ns[s];
+        blk = q;
+    }
+    return rev;
+}
+
+// w^r for r = 1..R-1 from w (registers only)
+template <typename T, int R> NW_HD void tw_powers(cx<T> w, cx<T>* p) {
+    p[1] = w;
+#pragma unroll
+    for (int r = 2; r < R; ++r) p[r] = cmul(p[r / 2], p[r - r / 2]);
+}
+
+template <typename T, int DIR> NW_HD cx<T> tw_dir(cx<T> w) { return DIR > 0 ? w : mk<T>(w.x, -w.y); }
+
+// ---- decimation in frequency ------------------------------------------------------------
+template <typename T, int R, int DIR, bool LAST, bool RAW, class Dst>
+NW_HD void dif_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
+                     const Dst& dst, int tid, int nthr) {
+    const int P = st.P;
+    const int L = P / st.ns[s];          // block length of this stage
+    const int Q = L / R;                 // butterflies per block = stride
+    const int tws = st.ns[s];            // P / L
+    const uint32_t nwork = (uint32_t)(P / R) << tpsh;
+    const int TP = 1 << tpsh;
+#pragma unroll 1
+    for (uint32_t lin = tid; lin < nwork; lin += nthr) {
+        const int tp = (int)(lin & (TP - 1));
+        const int bi = (int)(lin >> tpsh);
+        const int blk = LAST ? bi : (int)fd_div((uint32_t)bi, st.div_q[s]);   // bi / Q
+        const int np = bi - blk * Q;
+        cx2<T>* e = buf + (((size_t)blk * L + np) << tpsh) + tp;
+        const size_t stride = (size_t)Q << tpsh;
+        cx2<T> v[R];
+        typename Dst::Ctx ctx;
+        if (LAST) ctx = dst.begin(fft2_rev(st, blk), P / R, tp);   // issues the epilogue's own loads early
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = RAW ? raw_to_packed<T>(e[r * stride]) : e[r * stride];
+        B2<T, R, DIR>::run(v);
+        if (LAST) {
+            dst.template store_all<R>(ctx, v);
+        } else {
+            cx<T> w[R];
+            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * tws]), w);
+            e[0] = v[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) e[r * stride] = cmul_s(v[r], w[r]);
+        }
+    }
+}
+
+template <typename T, int DIR, bool LAST, bool RAW, class Dst>
+NW_HD void dif_stage_any(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
+                         const Dst& dst, int tid, int nthr) {
+    switch (st.radix[s]) {
+        case 2: dif_stage<T, 2, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 3: dif_stage<T, 3, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 4: dif_stage<T, 4, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 5: dif_stage<T, 5, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 6: dif_stage<T, 6, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 8: dif_stage<T, 8, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 10: dif_stage<T, 10, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 12: dif_stage<T, 12, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 15: dif_stage<T, 15, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 16: dif_stage<T, 16, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        default: break;
+    }
+}
+
+// buf holds the input in natural order on entry (visible to the CTA); results go to dst.
+// RAW0: the units of buf are two plain complex values {re0, im0, re1, im1} (a tile as it sits in
+// global memory) instead of lane-packed {re0, re1, im0, im1}; the first pass repacks in registers.
+template <typename T, int DIR, bool RAW0, class Dst>
+NW_HD void fft2_dif(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid,
+                    int nthr) {
+    if (st.nst == 1) {
+        dif_stage_any<T, DIR, true, RAW0>(st, 0, tpsh, tw, buf, dst, tid, nthr);
+        return;
+    }
+    dif_stage_any<T, DIR, false, RAW0>(st, 0, tpsh, tw, buf, dst, tid, nthr);
+    NW_SYNC();
+#pragma unroll 1
+    for (int s = 1; s < st.nst - 1; ++s) {
+        dif_stage_any<T, DIR, false, false>(st, s, tpsh, tw, buf, dst, tid, nthr);
+        NW_SYNC();
+    }
+    dif_stage_any<T, DIR, true, false>(st, st.nst - 1, tpsh, tw, buf, dst, tid, nthr);
+}
+
+// Src tag: the input already sits in buf at its decimation-in-time position (fft2_dit_pos)
+struct FromBuf {};
+template <class S> struct is_from_buf { static const bool value = false; };
+template <> struct is_from_buf<FromBuf> { static const bool value = true; };
+
+// slot of input element n for fft2_dit: butterfly blk = unrev(n mod step) of the first pass, input r = n / step
+NW_HD int fft2_dit_pos(const Fft2Plan& st, int n) {
+    const int rl = st.radix[st.nst - 1];
+    const int step = st.P / rl;
+    const int r = n / step;
+    int x = n - r * step, blk = 0;
+    for (int s = 0; s <= st.nst - 2; ++s) {
+        const int q = (int)fd_div((uint32_t)x, st.div_r[s]);
+        blk = blk * st.radix[s] + (x - q * st.radix[s]);
+        x = q;
+    }
+    return blk * rl + r;
+}
+
+// ---- decimation in time ---------------------------------------------------------------------
+// pass index q = 0 runs radix[nst-1] on contiguous groups, reading from Src at digit-reversed
+// indices; the last pass runs radix[0] at stride P / R_0 and writes natural-order results to Dst.
+template <typename T, int R, int DIR, bool FIRST, bool LAST, class Src, class Dst>
+NW_HD void dit_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
+                     const Dst& dst, int tid, int nthr) {
+    const int P = st.P;
+    const int L = P / st.ns[s];
+    const int Q = L / R;
+    const int tws = st.ns[s];
+    const uint32_t nwork = (uint32_t)(P / R) << tpsh;
+    const int TP = 1 << tpsh;
+#pragma unroll 1
+    for (uint32_t lin = tid; lin < nwork; lin += nthr) {
+        const int tp = (int)(lin & (TP - 1));
+        const int bi = (int)(lin >> tpsh);
+        const int blk = FIRST ? bi : (int)fd_div((uint32_t)bi, st.div_q[s]);
+        const int np = bi - blk * Q;
+        cx2<T>* e = buf + (((size_t)blk * L + np) << tpsh) + tp;
+        const size_t stride = (size_t)Q << tpsh;
+        cx2<T> v[R];
+        typename Dst::Ctx ctx;
+        if (LAST) ctx = dst.begin(np, Q, tp);   // blk == 0, L == P; issues the epilogue's own loads early
+        if (FIRST) {
+            if constexpr (is_from_buf<Src>::value) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[r] = e[r * stride];
+            } else {
+                src.template load_all<R>(fft2_rev(st, blk), P / R, tp, v);
+            }
+        } else {
+            cx<T> w[R];
+            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * tws]), w);
+            v[0] = e[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul_s(e[r * stride], w[r]);
+        }
+        B2<T, R, DIR>::run(v);
+        if (LAST) {
+            dst.template store_all<R>(ctx, v);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) e[r * stride] = v[r];
+        }
+    }
+}
+
+template <typename T, int DIR, bool FIRST, bool LAST, class Src, class Dst>
+NW_HD void dit_stage_any(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
+                         const Src& src, const Dst& dst, int tid, int nthr) {
+    switch (st.radix[s]) {
+        case 2: dit_stage<T, 2, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 3: dit_stage<T, 3, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 4: dit_stage<T, 4, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 5: dit_stage<T, 5, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 6: dit_stage<T, 6, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 8: dit_stage<T, 8, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 10: dit_stage<T, 10, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 12: dit_stage<T, 12, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 15: dit_stage<T, 15, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 16: dit_stage<T, 16, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        default: break;
+    }
+}
+
+// No barrier on entry or exit: the caller orders buf's reuse and dst's visibility.
+template <typename T, int DIR, class Src, class Dst>
+NW_HD void fft2_dit(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
+                    const Dst& dst, int tid, int nthr) {
+    const int m = st.nst;
+    if (m == 1) {
+        dit_stage_any<T, DIR, true, true>(st, 0, tpsh, tw, buf, src, dst, tid, nthr);
+        return;
+    }
+    dit_stage_any<T, DIR, true, false>(st, m - 1, tpsh, tw, buf, src, dst, tid, nthr);
+    NW_SYNC();
+    for (int s = m - 2; s >= 1; --s) {
+        dit_stage_any<T, DIR, false, false>(st, s, tpsh, tw, buf, src, dst, tid, nthr);
+        NW_SYNC();
+    }
+    dit_stage_any<T, DIR, false, true>(st, 0, tpsh, tw, buf, src, dst, tid, nthr);
+}
+
+}  // namespace nw

@@ -1,0 +1,217 @@
+// Kernel bodies of the fast long-row path (packed in-place engine, nw_fft2.cuh).
+//
+// Four-step split N = N1 * N2 (k = N2 k1 + k2, n = n1 + N1 n2), as in nw_kernels.cuh:
+//   passA2_body  columns: for TA = 2*TPA consecutive k2 of one (signal, frequency) row, spectrum
+//                generation x signal spectrum (base.py:236-248, 404) gathered straight into a
+//                decimation-in-time N1-point transform; natural-order results times w_N^{k2 n1}
+//                go to the L2-resident intermediate Tm in TB-blocked layout.
+//   passB2_body  rows: one bulk (TMA) copy brings a tile of TB = 2*TPB consecutive n1 x all k2 into
+//                shared memory, a decimation-in-frequency N2-point transform runs in place, and
+//                the |z|^2 / |z| / z epilogue (base.py:425, 443) stores straight from registers -
+//                each n2 gives TB consecutive output samples (32-byte sectors for fp32, TB = 8).
+// Both bodies compile for the host as well (tests/emul steps them block by block).
+#pragma once
+#include "nw_common.h"
+#include "nw_fft2.cuh"
+#include "nw_family.cuh"
+#include "nw_kernels.cuh"
+
+namespace nw {
+
+template <typename T>
+struct Long2Params {
+    long long N;
+    int N1, N2, F;
+    int tpshA;          // pass A: 2 << tpshA columns per CTA
+    int tpshB;          // pass B: 2 << tpshB rows (n1) per CTA
+    Fft2Plan stA, stB;
+    const cx<T>* twA;   // [N1]
+    const cx<T>* twB;   // [N2]
+    const cx<T>* twH;   // w_N^{j << lb}
+    const cx<T>* twL;   // w_N^{j}, j < 1 << lb
+    int lb;
+    const cx<T>* X;     // spectra of the signals of this group, [nsig][N]
+    cx<T>* Tm;          // intermediate ring, [rows][tm_stride]
+    long long tm_stride;
+    void* out;          // output of row 0 of the group
+    int row0;           // first row (signal-major: row = signal * F + frequency) of this launch
+    int out_mode;
+    SpecParams<T> sp;
+};
+
+template <typename T> NW_HD cx<T> big_twiddle2(const Long2Params<T>& P, int m) {
+    const cx<T> a = P.twH[m >> P.lb];
+    const cx<T> b = P.twL[m & ((1 << P.lb) - 1)];
+    return cmul(a, b);
+}
+
+// ---- pass A --------------------------------------------------------------------------------
+// natural-order results n1 = base + q * step of columns k2, k2 + 1, times w_N^{k2 n1}: the factor runs
+// as a geometric sequence in q (ratio w_N^{k2 step}), two table look-ups per lane and butterfly
+template <typename T> struct TmDst2 {
+    const Long2Params<T>* P;
+    cx<T>* tm;
+    int c;
+    struct Ctx {
+        cx2<T> cur, g;
+        cx<T>* col;
+        uint32_t n1, step;
+        bool valid, two;
+    };
+    NW_HD Ctx begin(int base, int step, int tp) const {
+        Ctx x;
+        const int N2 = P->N2;
+        const int k2 = c + 2 * tp;
+        x.valid = k2 < N2;
+        x.two = k2 + 1 < N2;
+        const int k2a = x.valid ? k2 : 0, k2b = x.two ? k2 + 1 : k2a;
+        x.cur = mk2<T>(big_twiddle2<T>(*P, k2a * base), big_twiddle2<T>(*P, k2b * base));
+        x.g = mk2<T>(big_twiddle2<T>(*P, k2a * step), big_twiddle2<T>(*P, k2b * step));
+        x.col = tm + ((size_t)k2a << (P->tpshB + 1));
+        x.n1 = (uint32_t)base;
+        x.step = (uint32_t)step;
+        return x;
+    }
+    template <int R> NW_HD void store_all(const Ctx& x, const cx2<T>* v) const {
+        if (!x.valid) return;
+        const int shB = P->tpshB + 1;
+        const uint32_t mask = (1u << shB) - 1u;
+        const uint32_t blk = (uint32_t)P->N2 << shB;        // elements per block of 2^shB rows
+        cx2<T> cur = x.cur;
+        uint32_t n1 = x.n1;
+#pragma unroll
+        for (int q = 0; q < R; ++q, n1 += x.step) {
+            const cx2<T> y = cmul_p(v[q], cur);
+            if (q + 1 < R) cur = cmul_p(cur, x.g);
+            cx<T>* o = x.col + (size_t)((n1 >> shB) * blk + (n1 & mask));
+            o[0] = lane0(y);
+            if (x.two) o[(size_t)1 << shB] = lane1(y);
+        }
+    }
+};
+
+template <typename T> NW_HD size_t passA2_smem_bytes(int N1, int tpsh) { return ((size_t)N1 << tpsh) * sizeof(cx2<T>); }
+template <typename T> NW_HD size_t passB2_smem_bytes(int N2, int tpsh) { return ((size_t)N2 << tpsh) * sizeof(cx2<T>) + 16; }
+
+// The tile's input - spectrum x signal spectrum on the non-zero band only - is gathered into the
+// transform's shared-memory slots by a compact loop (one evaluation per in-band bin, nothing unrolled
+// around the formula), the rest of the tile is zero.
+template <typename T>
+NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
+    cx2<T>* buf = (cx2<T>*)smem;
+    const int tpsh = P.tpshA, TP = 1 << tpsh;
+    const int c = bx << (tpsh + 1);
+    const int gr = P.row0 + by;
+    const int si = gr / P.F, fi = gr - si * P.F;
+    const int N1 = P.N1, N2 = P.N2;
+    const FreqRec rec = P.sp.rec[fi];
+    const cx<T>* X = P.X + (size_t)si * (size_t)P.N;
+    // rows k1 of this tile that hold a non-zero bin k = k1 N2 + k2, k2 in [c, c + 2 TP)
+    const int clast = (c + 2 * TP < N2 ? c + 2 * TP : N2) - 1;
+    int k1lo = rec.lo > clast ? (rec.lo - clast + N2 - 1) / N2 : 0;
+    int k1hi = rec.hi - 1 >= c ? (rec.hi - 1 - c) / N2 : -1;
+    if (k1hi > N1 - 1) k1hi = N1 - 1;
+    const int nk1 = k1hi - k1lo + 1;
+    const cx2<T> z = zero2<T>();
+    for (int i = tid; i < (N1 << tpsh); i += nthr) buf[i] = z;
+    NW_SYNC();
+    for (int i = tid; i < (nk1 << tpsh); i += nthr) {
+        const int tp = i & (TP - 1);
+        const int k1 = k1lo + (i >> tpsh);
+        const int k2 = c + 2 * tp;
+        const int k = k1 * N2 + k2;
+        cx<T> a = mk<T>((T)0, (T)0), b = a;
+        if (k2 < N2 && k >= rec.lo && k < rec.hi) a = spec_times<T>(P.sp, rec, fi, k, X[k]);
+        if (k2 + 1 < N2 && k + 1 >= rec.lo && k + 1 < rec.hi) b = spec_times<T>(P.sp, rec, fi, k + 1, X[k + 1]);
+        buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(a, b);
+    }
+    NW_SYNC();
+    TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c};
+    fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
+}
+
+// ---- pass B --------------------------------------------------------------------------------
+// results n2 = base + q * step of rows n1 = r0 + 2 tp, + 1  ->  out[n1 + N1 n2]
+template <typename T, int MODE> struct LongOutDst2 {
+    void* out;       // row base
+    int N1, r0;
+    bool vec_ok;     // N1 even: pairs of consecutive samples are 2*sizeof(T) aligned
+    struct Ctx {
+        size_t idx, dstep;
+        bool valid, two;
+    };
+    NW_HD Ctx begin(int base, int step, int tp) const {
+        Ctx x;
+        const int n1 = r0 + 2 * tp;
+        x.valid = n1 < N1;
+        x.two = n1 + 1 < N1;
+        x.idx = (size_t)n1 + (size_t)N1 * (size_t)base;
+        x.dstep = (size_t)N1 * (size_t)step;
+        return x;
+    }
+    template <int R> NW_HD void store_all(const Ctx& x, const cx2<T>* v) const {
+        if (!x.valid) return;
+        const bool two = x.two;
+        const size_t idx = x.idx, dstep = x.dstep;
+        if (MODE == OUT_CWT) {
+            cx<T>* o = (cx<T>*)out + idx;
+#pragma unroll
+            for (int q = 0; q < R; ++q, o += dstep) {
+                o[0] = lane0(v[q]);
+                if (two) o[1] = lane1(v[q]);
+            }
+            return;
+        }
+        T* o = (T*)out + idx;
+        if (two && vec_ok) {
+#pragma unroll
+            for (int q = 0; q < R; ++q, o += dstep) {
+                if (MODE == OUT_POWER) {
+                    const pk<T> p = pk_fma(v[q].im, v[q].im, v[q].re * v[q].re);
+                    *(cx<T>*)o = mk<T>(pk_lo(p), pk_hi(p));   // one 2*sizeof(T) store
+                } else {
+                    *(cx<T>*)o = mk<T>(nw_hypot(pk_lo(v[q].re), pk_lo(v[q].im)), nw_hypot(pk_hi(v[q].re), pk_hi(v[q].im)));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q, o += dstep) {
+                o[0] = real_out<T>(MODE, lane0(v[q]));
+                if (two) o[1] = real_out<T>(MODE, lane1(v[q]));
+            }
+        }
+    }
+};
+
+template <typename T, int MODE>
+NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
+    const int shB = P.tpshB + 1;
+    const int TB = 1 << shB;
+    cx2<T>* buf = (cx2<T>*)smem;
+    const size_t tile_elems = (size_t)P.N2 << shB;   // complex values
+    const cx<T>* tile = P.Tm + (size_t)by * P.tm_stride + (size_t)bx * tile_elems;
+#if defined(__CUDA_ARCH__)
+    const size_t bytes = tile_elems * sizeof(cx<T>);
+    uint64_t* bar = (uint64_t*)((char*)smem + bytes);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)bytes);
+        const size_t CH = 32768;
+        for (size_t off = 0; off < bytes; off += CH) {
+            const size_t n = bytes - off < CH ? bytes - off : CH;
+            bulk_g2s((char*)smem + off, (const char*)tile + off, (uint32_t)n, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+#else
+    for (size_t i = tid; i < tile_elems; i += nthr) ((cx<T>*)smem)[i] = tile[i];
+    NW_SYNC();
+#endif
+    const int gr = P.row0 + by;
+    const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
+    LongOutDst2<T, MODE> dst{(char*)P.out + (size_t)gr * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
+    fft2_dif<T, +1, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
+}
+
+}  // namespace nw

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "nw_kernels.cuh"
+#include "nw_kernels2.cuh"
 
 namespace nw {
 template <typename T> cudaError_t prepare_short();
@@ -15,4 +16,10 @@ template <typename T>
 cudaError_t launch_passA(int dir, const LongParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
 template <typename T>
 cudaError_t launch_passB(int dir, const LongParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+// fast long-row path (nw_kernels2.cuh); CFG = compiled launch shape (nw_plan.h CFG2_*)
+template <typename T, int CFG> cudaError_t prepare_long2();
+template <typename T, int CFG>
+cudaError_t launch_passA2(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+template <typename T, int CFG>
+cudaError_t launch_passB2(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
 }  // namespace nw

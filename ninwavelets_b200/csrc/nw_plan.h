@@ -6,6 +6,7 @@
 // the C ABI without a GPU.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -45,6 +46,15 @@ struct HostPlan {
     int nthr_short = 256, nthr_long = 512;
     long long tm_stride = 0;
     int ring = 1;                // rows (and signals) in flight on the long path
+    // fast long path (packed in-place engine, nw_kernels2.cuh); 0 = not available for this N
+    int fast = 0;
+    int N1f = 0, N2f = 0, tpshA = 0, tpshB = 0;
+    Fft2Plan stA2{}, stB2{};
+    int nthrA2 = 256, nthrB2 = 256;
+    int cfgA = 0, cfgB = 0;      // compiled launch shape (CFG2_*) of each pass
+    size_t smem_A2 = 0, smem_B2 = 0;
+    long long tm_stride2 = 0;
+    int ring2 = 1;               // rows per pass-A / pass-B launch pair
 };
 
 inline size_t cx_size(int dtype) { return dtype == 0 ? 8 : 16; }
@@ -83,6 +93,70 @@ inline bool factorise(long long P, FftStages& st, std::string& err) {
         st.ns[i] = ns;
         st.div_ns[i] = make_fastdiv((uint32_t)ns);
         st.div_pr[i] = make_fastdiv((uint32_t)(P / rad[i]));
+        ns *= rad[i];
+    }
+    return true;
+}
+
+// ---- radix plan of the packed in-place engine (nw_fft2.cuh) -----------------------------------
+// P = 2^a 3^b 5^c is covered by radices {16,15,12,10,8,6,5,4,3,2}: fewest stages first (every stage is
+// one round trip of the tile through shared memory), then least butterfly arithmetic per point.
+// An odd radix, when there is one, goes last: the stride-1 pass then reads R-element groups whose
+// shared-memory footprint is conflict free for two butterflies per quarter warp.
+inline bool plan_packed(long long P, Fft2Plan& out) {
+    if (P < 2 || P > (1 << 16)) return false;
+    int e[3] = {0, 0, 0};
+    long long m = P;
+    while (m % 2 == 0) { m /= 2; ++e[0]; }
+    while (m % 3 == 0) { m /= 3; ++e[1]; }
+    while (m % 5 == 0) { m /= 5; ++e[2]; }
+    if (m != 1) return false;
+    static const int RAD[10] = {16, 15, 12, 10, 8, 6, 5, 4, 3, 2};
+    static const int EXP[10][3] = {{4,0,0},{0,1,1},{2,1,0},{1,0,1},{3,0,0},{1,1,0},{0,0,1},{2,0,0},{0,1,0},{1,0,0}};
+    // packed ops per point of each butterfly plus ~3.5 for the twiddle multiply of a non-final stage
+    static const double COST[10] = {10.0, 11.2, 7.0, 9.2, 7.0, 6.0, 7.2, 4.0, 4.0, 2.0};
+    struct Best { int stages; double cost; std::vector<int> rad; };
+    const int A = e[0] + 1, B = e[1] + 1, C = e[2] + 1;
+    std::vector<Best> best((size_t)A * B * C);
+    std::vector<char> done((size_t)A * B * C, 0);
+    auto idx = [&](int a, int b, int c) { return ((size_t)a * B + b) * C + c; };
+    best[idx(0, 0, 0)] = Best{0, 0.0, {}};
+    done[idx(0, 0, 0)] = 1;
+    for (int a = 0; a < A; ++a)
+        for (int b = 0; b < B; ++b)
+            for (int c = 0; c < C; ++c) {
+                if (a == 0 && b == 0 && c == 0) continue;
+                Best bb{1 << 20, 1e300, {}};
+                for (int i = 0; i < 10; ++i) {
+                    const int pa = a - EXP[i][0], pb = b - EXP[i][1], pc = c - EXP[i][2];
+                    if (pa < 0 || pb < 0 || pc < 0 || !done[idx(pa, pb, pc)]) continue;
+                    const Best& prev = best[idx(pa, pb, pc)];
+                    const int st = prev.stages + 1;
+                    const double cost = prev.cost + COST[i] + 3.5;
+                    if (st < bb.stages || (st == bb.stages && cost < bb.cost - 1e-9)) {
+                        bb.stages = st;
+                        bb.cost = cost;
+                        bb.rad = prev.rad;
+                        bb.rad.push_back(RAD[i]);
+                    }
+                }
+                if (bb.stages < (1 << 20)) { best[idx(a, b, c)] = bb; done[idx(a, b, c)] = 1; }
+            }
+    const Best& r = best[idx(e[0], e[1], e[2])];
+    if (!done[idx(e[0], e[1], e[2])] || r.stages > MAX_STAGES2) return false;
+    std::vector<int> rad = r.rad;
+    std::sort(rad.begin(), rad.end(), [](int x, int y) { return x > y; });
+    for (size_t i = 0; i < rad.size(); ++i)
+        if (rad[i] & 1) { std::swap(rad[i], rad.back()); break; }   // one odd radix last
+    out.P = (int)P;
+    out.nst = (int)rad.size();
+    int ns = 1;
+    for (int i = 0; i < out.nst; ++i) {
+        out.radix[i] = rad[i];
+        out.ns[i] = ns;
+        const int L = (int)(P / ns);
+        out.div_q[i] = make_fastdiv((uint32_t)(L / rad[i]));
+        out.div_r[i] = make_fastdiv((uint32_t)rad[i]);
         ns *= rad[i];
     }
     return true;
@@ -236,6 +310,113 @@ inline void plan_bands(HostPlan& hp) {
 // ---- execution shape -----------------------------------------------------------------
 inline int ilog2_floor(long long v) { int l = 0; while ((1LL << (l + 1)) <= v) ++l; return l; }
 
+// Launch shapes the fast kernels are compiled for: {max threads, min resident CTAs} -> register cap.
+// A tile's thread count and shape are chosen together: every stage has (P / R_s) << tpsh butterflies;
+// take the multiple of 32 that wastes the fewest thread slots over all stages, weighted by how many
+// threads the shape keeps resident per SM (shared memory and registers), with a small bonus for the
+// shape with more registers per thread.
+static const int N_CFG2 = 4;
+static const int CFG2_MAXTHR[N_CFG2] = {256, 224, 128, 64};
+static const int CFG2_MINCTA[N_CFG2] = {3, 3, 5, 8};
+static const int CFG2_MAXREG[N_CFG2] = {80, 96, 96, 128};   // __maxnreg__ of the compiled kernels
+inline int cfg2_regcap(int c) { return CFG2_MAXREG[c]; }
+
+inline void pick_threads2(const Fft2Plan& st, int tpsh, size_t smem, int ncfg, int& nthr, int& cfg) {
+    // Measured on B200 (profiles/r01/shape_sweep.md): with room for >= 5 tiles per SM, 128-thread CTAs at
+    // 96 registers win (more independent CTAs to overlap load, butterfly and store phases); with 3-4 tiles
+    // per SM the most threads win over more registers; tiny tiles take 64-thread CTAs.
+    const int by_smem = (int)std::min<size_t>(16, (SMEM_MAX + 1024) / (smem + 1024));
+    long long maxnb = 0;
+    for (int s = 0; s < st.nst; ++s) maxnb = std::max(maxnb, (long long)(st.P / st.radix[s]) << tpsh);
+    cfg = 0;
+    if (ncfg > 1) {
+        if (maxnb <= 64 && by_smem >= 8) cfg = 3;
+        else if (by_smem >= 5 || maxnb <= 128) cfg = 2;
+    }
+    const int maxthr = CFG2_MAXTHR[cfg];
+    if (cfg == 0) {   // fill the shape: more warps beat a better fit of butterflies to threads here
+        nthr = (int)std::min<long long>(maxthr, (maxnb + 31) / 32 * 32);
+        return;
+    }
+    const int lo = std::max(32, (int)std::min<long long>(maxthr * 3 / 4, (maxnb + 31) / 32 * 32) / 32 * 32);
+    double best = -1;
+    nthr = maxthr;
+    for (int nt = maxthr; nt >= lo; nt -= 32) {   // larger first: ties go to more threads
+        double work = 0, slots = 0;
+        for (int s = 0; s < st.nst; ++s) {
+            const long long nb = (long long)(st.P / st.radix[s]) << tpsh;
+            work += (double)nb * st.radix[s];
+            slots += (double)((nb + nt - 1) / nt) * nt * st.radix[s];
+        }
+        const double e = work / slots * (0.5 + 0.5 * nt / maxthr);
+        if (e > best + 1e-9) { best = e; nthr = nt; }
+    }
+}
+
+inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+// Fast long path: N = N1 * N2 with both factors 2-3-5 smooth; tiles sized for three CTAs per SM.
+inline void plan_shape_fast(HostPlan& hp) {
+    const size_t cs = cx_size(hp.dtype);
+    const long long N = hp.N;
+    hp.fast = 0;
+    double bestScore = -1e300;
+    auto ctas = [&](size_t bytes) { return bytes <= 75 * 1024 ? 3 : bytes <= SMEM_HALF ? 2 : bytes <= SMEM_MAX ? 1 : 0; };
+    for (long long d = 2; d * d <= N; ++d) {
+        if (N % d) continue;
+        const long long cand[2] = {d, N / d};
+        for (int w = 0; w < 2; ++w) {
+            const long long n1 = cand[w], n2 = N / n1;
+            if (w == 1 && n1 == n2) continue;
+            if (n1 > 32768 || n2 > 32768) continue;
+            Fft2Plan a, b;
+            if (!plan_packed(n1, a) || !plan_packed(n2, b)) continue;
+            const int fa = env_int("NWCWT_TPSH_A", -1), fb = env_int("NWCWT_TPSH_B", -1);   // tuning overrides
+            for (int ta = 2; ta >= 0; --ta)
+                for (int tb = 2; tb >= 0; --tb) {
+                    if ((fa >= 0 && ta != fa) || (fb >= 0 && tb != fb)) continue;
+                    const size_t ba = ((size_t)n1 << ta) * 2 * cs, bb = ((size_t)n2 << tb) * 2 * cs + 16;
+                    const int ca = ctas(ba), cb = ctas(bb);
+                    if (!ca || !cb) continue;
+                    double score = 100.0 * (ta + tb) + 60.0 * (ca + cb) - 40.0 * (a.nst + b.nst);
+                    for (int i = 0; i < a.nst; ++i) if (a.radix[i] >= 15) score -= 25.0;   // register pressure
+                    for (int i = 0; i < b.nst; ++i) if (b.radix[i] >= 15) score -= 25.0;
+                    if (n1 & 1) score -= 30.0;                 // unaligned output pairs
+                    if (n2 >= n1) score += 5.0;
+                    score -= 10.0 * fabs(log2((double)n1 / (double)n2));
+                    if (score > bestScore) {
+                        bestScore = score;
+                        hp.fast = 1;
+                        hp.N1f = (int)n1; hp.N2f = (int)n2; hp.tpshA = ta; hp.tpshB = tb;
+                        hp.stA2 = a; hp.stB2 = b;
+                        hp.smem_A2 = ba; hp.smem_B2 = bb;
+                    }
+                }
+        }
+    }
+    if (!hp.fast) return;
+    const int ncfg = hp.dtype == 0 ? N_CFG2 : 1;   // fp64 kernels exist in shape 0 only
+    pick_threads2(hp.stA2, hp.tpshA, hp.smem_A2, ncfg, hp.nthrA2, hp.cfgA);
+    pick_threads2(hp.stB2, hp.tpshB, hp.smem_B2, ncfg, hp.nthrB2, hp.cfgB);
+    if (hp.dtype == 0) {   // tuning overrides (fp32 shapes only)
+        hp.nthrA2 = env_int("NWCWT_NTHR_A", hp.nthrA2);
+        hp.nthrB2 = env_int("NWCWT_NTHR_B", hp.nthrB2);
+        hp.cfgA = env_int("NWCWT_CFG_A", hp.cfgA);
+        hp.cfgB = env_int("NWCWT_CFG_B", hp.cfgB);
+    }
+    const int TB = 2 << hp.tpshB;
+    const long long nblk = (hp.N1f + TB - 1) / TB;
+    hp.tm_stride2 = nblk * hp.N2f * TB;
+    const size_t slot = (size_t)hp.tm_stride2 * cs;
+    size_t ring_mb = 48;                                  // per stream slot; two slots are in flight
+    if (const char* e = getenv("NWCWT_RING_MB")) ring_mb = (size_t)std::max(1, atoi(e));
+    long long ring = (long long)((ring_mb << 20) / slot);
+    hp.ring2 = (int)std::max<long long>(1, std::min<long long>(ring, 256));
+}
+
 inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) {
     const size_t cs = cx_size(hp.dtype);
     const long long N = hp.N;
@@ -307,6 +488,7 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
     const size_t slot = (size_t)hp.tm_stride * cs;
     long long ring = (long long)((48u << 20) / slot);
     hp.ring = (int)std::max<long long>(1, std::min<long long>(ring, 64));
+    plan_shape_fast(hp);
     return true;
 }
 

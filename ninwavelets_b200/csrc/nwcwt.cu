@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) nwcwt_reduce_kernel(const void* in, T* ou
 // plan object
 // ---------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static bool g_force_generic = false;   // nwcwt_debug_force_generic: run the generic kernels even where a fast path exists
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -86,6 +88,13 @@ struct nwcwt_plan {
     bool on_device = false;
     // device tables
     void *d_tw = nullptr, *d_twA = nullptr, *d_twB = nullptr, *d_twH = nullptr, *d_twL = nullptr;
+    void *d_twA2 = nullptr, *d_twB2 = nullptr;   // fast long path
+    // fast long path: launch pairs of consecutive row groups alternate between auxiliary streams so
+    // that one group's pass A fills the SMs the previous group's pass-B tail leaves idle
+    static const int MAX_AUX = 4;
+    cudaStream_t aux[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
+    int n_aux = 0;
     void* d_rec = nullptr;
     void* d_table = nullptr;
     // host-call resources
@@ -145,6 +154,44 @@ static void fill_twiddles(std::vector<cx<T>>& v, long long count, long long P, l
     }
 }
 
+// fast long path: compiled launch shapes per precision (k_long2_*.cu)
+template <typename T> struct Long2Dispatch;
+template <> struct Long2Dispatch<float> {
+    static cudaError_t prepare(int c) {
+        switch (c) {
+            case 1: return prepare_long2<float, 1>();
+            case 2: return prepare_long2<float, 2>();
+            case 3: return prepare_long2<float, 3>();
+            default: return prepare_long2<float, 0>();
+        }
+    }
+    static cudaError_t A(int c, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        switch (c) {
+            case 1: return launch_passA2<float, 1>(P, g, nt, sm, s);
+            case 2: return launch_passA2<float, 2>(P, g, nt, sm, s);
+            case 3: return launch_passA2<float, 3>(P, g, nt, sm, s);
+            default: return launch_passA2<float, 0>(P, g, nt, sm, s);
+        }
+    }
+    static cudaError_t B(int c, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        switch (c) {
+            case 1: return launch_passB2<float, 1>(P, g, nt, sm, s);
+            case 2: return launch_passB2<float, 2>(P, g, nt, sm, s);
+            case 3: return launch_passB2<float, 3>(P, g, nt, sm, s);
+            default: return launch_passB2<float, 0>(P, g, nt, sm, s);
+        }
+    }
+};
+template <> struct Long2Dispatch<double> {
+    static cudaError_t prepare(int) { return prepare_long2<double, 0>(); }
+    static cudaError_t A(int, const Long2Params<double>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        return launch_passA2<double, 0>(P, g, nt, sm, s);
+    }
+    static cudaError_t B(int, const Long2Params<double>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        return launch_passB2<double, 0>(P, g, nt, sm, s);
+    }
+};
+
 template <typename T>
 static int upload_tw(void** dptr, long long count, long long P, long long step) {
     std::vector<cx<T>> v;
@@ -168,6 +215,10 @@ static int ensure_device_t(nwcwt_plan* pl) {
         const long long nL = 1LL << hp.lb, nH = (hp.N + nL - 1) / nL;
         if ((rc = upload_tw<T>(&pl->d_twL, nL, hp.N, 1))) return rc;
         if ((rc = upload_tw<T>(&pl->d_twH, nH, hp.N, nL))) return rc;
+        if (hp.fast) {
+            if ((rc = upload_tw<T>(&pl->d_twA2, hp.N1f, hp.N1f, 1))) return rc;
+            if ((rc = upload_tw<T>(&pl->d_twB2, hp.N2f, hp.N2f, 1))) return rc;
+        }
     }
     if (hp.F > 0) {
         CUDA_TRY(cudaMalloc(&pl->d_rec, sizeof(FreqRec) * hp.F));
@@ -189,6 +240,21 @@ static int ensure_device_t(nwcwt_plan* pl) {
     } else {
         CUDA_TRY(prepare_passA<T>());
         CUDA_TRY(prepare_passB<T>());
+        if (hp.fast) {
+            CUDA_TRY(Long2Dispatch<T>::prepare(hp.cfgA));
+            CUDA_TRY(Long2Dispatch<T>::prepare(hp.cfgB));
+            int ns = 2;
+            if (const char* e = getenv("NWCWT_STREAMS")) ns = atoi(e);
+            ns = ns < 1 ? 1 : ns > nwcwt_plan::MAX_AUX ? nwcwt_plan::MAX_AUX : ns;
+            if (ns > 1) {
+                for (int i = 0; i < ns; ++i) {
+                    CUDA_TRY(cudaStreamCreateWithFlags(&pl->aux[i], cudaStreamNonBlocking));
+                    CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join[i], cudaEventDisableTiming));
+                }
+                CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+                pl->n_aux = ns;
+            }
+        }
     }
     pl->on_device = true;
     return 0;
@@ -286,14 +352,46 @@ static LongParams<T> make_long(nwcwt_plan* pl) {
     return P;
 }
 
-// workspace layout of the long path: [ring] spectra of N, then [ring] Tm slots
+// intermediate ring of the long path: the forward transforms use the generic two-pass kernels,
+// the inverse ones the fast kernels when the plan has them; one region serves both
+static size_t tm_ring_bytes(const HostPlan& hp) {
+    const size_t cs = cx_size(hp.dtype);
+    size_t b = (size_t)hp.ring * hp.tm_stride * cs;
+    if (hp.fast) b = std::max<size_t>(b, (size_t)nwcwt_plan::MAX_AUX * (size_t)hp.ring2 * (size_t)hp.tm_stride2 * cs);
+    return align_up(b, 256);
+}
+
+template <typename T>
+static Long2Params<T> make_long2(nwcwt_plan* pl) {
+    const HostPlan& hp = pl->hp;
+    Long2Params<T> P;
+    memset(&P, 0, sizeof(P));
+    P.N = hp.N;
+    P.N1 = hp.N1f;
+    P.N2 = hp.N2f;
+    P.F = hp.F;
+    P.tpshA = hp.tpshA;
+    P.tpshB = hp.tpshB;
+    P.stA = hp.stA2;
+    P.stB = hp.stB2;
+    P.twA = (const cx<T>*)pl->d_twA2;
+    P.twB = (const cx<T>*)pl->d_twB2;
+    P.twH = (const cx<T>*)pl->d_twH;
+    P.twL = (const cx<T>*)pl->d_twL;
+    P.lb = hp.lb;
+    P.tm_stride = hp.tm_stride2;
+    P.sp = make_spec<T>(pl);
+    return P;
+}
+
+// workspace layout of the long path: [ring] spectra of N, then the Tm ring
 template <typename T>
 static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spectra_out, long long S, int output,
                        int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
                        bool forward_only) {
     const HostPlan& hp = pl->hp;
     const size_t xbytes = align_up((size_t)hp.ring * hp.N * sizeof(cx<T>), 256);
-    const size_t tbytes = align_up((size_t)hp.ring * hp.tm_stride * sizeof(cx<T>), 256);
+    const size_t tbytes = tm_ring_bytes(hp);
     if (ws_bytes < xbytes + tbytes || !ws) return fail(NWCWT_ERR_WORKSPACE, "workspace too small");
     cx<T>* X = (cx<T>*)ws;
     cx<T>* Tm = (cx<T>*)((char*)ws + xbytes);
@@ -310,6 +408,42 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
         { LaunchScope ls(1, stream); CUDA_TRY(launch_passA<T>(-1, P, dim3(tilesA, gs), hp.nthr_long, hp.smem_A, stream)); }
         { LaunchScope ls(2, stream); CUDA_TRY(launch_passB<T>(-1, P, dim3(tilesB, gs), hp.nthr_long, hp.smem_B, stream)); }
         if (forward_only) continue;
+        if (hp.fast && !g_force_generic) {
+            // inverse transforms of all gs * F rows of the group, ring2 rows per launch pair
+            Long2Params<T> Q = make_long2<T>(pl);
+            Q.X = X;
+            Q.Tm = Tm;
+            Q.out = (char*)out + (size_t)s0 * hp.F * (size_t)hp.N * esz;
+            Q.out_mode = output;
+            const unsigned tA = (unsigned)((hp.N2f + (2 << hp.tpshA) - 1) / (2 << hp.tpshA));
+            const unsigned tB = (unsigned)((hp.N1f + (2 << hp.tpshB) - 1) / (2 << hp.tpshB));
+            const long long rows = (long long)gs * hp.F;
+            const int ns = pl->n_aux;
+            if (ns > 1) {
+                CUDA_TRY(cudaEventRecord(pl->ev_fork, stream));
+                for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(pl->aux[i], pl->ev_fork, 0));
+            }
+            int gi = 0;
+            for (long long r0 = 0; r0 < rows; r0 += hp.ring2, ++gi) {
+                const int g = (int)std::min<long long>(hp.ring2, rows - r0);
+                const int slot = ns > 1 ? gi % ns : 0;
+                cudaStream_t st = ns > 1 ? pl->aux[slot] : stream;
+                Q.row0 = (int)r0;
+                Q.Tm = Tm + (size_t)slot * (size_t)hp.ring2 * (size_t)hp.tm_stride2;
+                { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, Q, dim3(tA, g), hp.nthrA2, hp.smem_A2, st)); }
+                { LaunchScope ls(4, st); CUDA_TRY(Long2Dispatch<T>::B(hp.cfgB, Q, dim3(tB, g), hp.nthrB2, hp.smem_B2, st)); }
+            }
+            if (ns > 1)
+                for (int i = 0; i < ns; ++i) {
+                    CUDA_TRY(cudaEventRecord(pl->ev_join[i], pl->aux[i]));
+                    CUDA_TRY(cudaStreamWaitEvent(stream, pl->ev_join[i], 0));
+                }
+            if (bl != NWCWT_BL_NONE) {
+                LaunchScope ls(5, stream);
+                nwcwt_baseline_rows_kernel<T><<<(unsigned)rows, 512, 0, stream>>>((T*)Q.out, hp.N, bl, (int)blo, (int)bhi);
+            }
+            continue;
+        }
         for (int si = 0; si < gs; ++si) {
             P.X = X + (size_t)si * hp.N;
             char* out_s = (char*)out + (size_t)(s0 + si) * hp.F * (size_t)hp.N * esz;
@@ -362,6 +496,11 @@ extern "C" {
 
 int nwcwt_version(void) { return NWCWT_VERSION; }
 int64_t nwcwt_launch_count(void) { return g_launches.load(); }
+
+int nwcwt_debug_force_generic(int32_t on) {
+    g_force_generic = on != 0;
+    return 0;
+}
 
 int nwcwt_profile_enable(int32_t on) {
     g_profile = on != 0;
@@ -441,12 +580,17 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
     if (!pl) return 0;
     if (pl->on_device || pl->h_stream[0]) {
         cudaSetDevice(pl->hp.device);
-        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table,
+        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_twA2, pl->d_twB2,
                         pl->h_in_dev[0], pl->h_in_dev[1], pl->h_out_dev[0], pl->h_out_dev[1], pl->h_ws[0], pl->h_ws[1]};
         for (void* p : ptrs)
             if (p) cudaFree(p);
         for (int i = 0; i < 2; ++i)
             if (pl->h_stream[i]) cudaStreamDestroy(pl->h_stream[i]);
+        for (int i = 0; i < nwcwt_plan::MAX_AUX; ++i) {
+            if (pl->aux[i]) cudaStreamDestroy(pl->aux[i]);
+            if (pl->ev_join[i]) cudaEventDestroy(pl->ev_join[i]);
+        }
+        if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
     }
     delete pl;
     return 0;
@@ -465,6 +609,20 @@ int nwcwt_plan_get_info(const nwcwt_plan* pl, nwcwt_plan_info* info) {
         info->n_stages[0] = hp.st.nst;
         for (int i = 0; i < hp.st.nst; ++i) info->radices[0][i] = hp.st.radix[i];
         info->smem_bytes = (int64_t)hp.smem_short;
+        info->threads[0] = hp.nthr_short;
+    } else if (hp.fast) {
+        info->n1 = hp.N1f;
+        info->n2 = hp.N2f;
+        info->batch = 2 << hp.tpshB;
+        info->n_stages[0] = hp.stA2.nst;
+        info->n_stages[1] = hp.stB2.nst;
+        for (int i = 0; i < hp.stA2.nst; ++i) info->radices[0][i] = hp.stA2.radix[i];
+        for (int i = 0; i < hp.stB2.nst; ++i) info->radices[1][i] = hp.stB2.radix[i];
+        info->smem_bytes = (int64_t)std::max(hp.smem_A2, hp.smem_B2);
+        info->path = 2;
+        info->threads[0] = hp.nthrA2;
+        info->threads[1] = hp.nthrB2;
+        info->rows_per_launch = hp.ring2;
     } else {
         info->n1 = hp.N1;
         info->n2 = hp.N2;
@@ -474,6 +632,8 @@ int nwcwt_plan_get_info(const nwcwt_plan* pl, nwcwt_plan_info* info) {
         for (int i = 0; i < hp.stA.nst; ++i) info->radices[0][i] = hp.stA.radix[i];
         for (int i = 0; i < hp.stB.nst; ++i) info->radices[1][i] = hp.stB.radix[i];
         info->smem_bytes = (int64_t)std::max(hp.smem_A, hp.smem_B);
+        info->threads[0] = info->threads[1] = hp.nthr_long;
+        info->rows_per_launch = hp.ring;
     }
     return 0;
 }
@@ -496,7 +656,7 @@ int nwcwt_workspace_bytes(const nwcwt_plan* pl, int64_t n_signals, size_t* bytes
         return 0;
     }
     const size_t cs = cx_size(hp.dtype);
-    *bytes = align_up((size_t)hp.ring * hp.N * cs, 256) + align_up((size_t)hp.ring * hp.tm_stride * cs, 256);
+    *bytes = align_up((size_t)hp.ring * hp.N * cs, 256) + tm_ring_bytes(hp);
     return 0;
 }
 

@@ -14,9 +14,58 @@
 #include "../../ninwavelets_b200/csrc/nw_fft.cuh"
 #include "../../ninwavelets_b200/csrc/nw_family.cuh"
 #include "../../ninwavelets_b200/csrc/nw_kernels.cuh"
+#include "../../ninwavelets_b200/csrc/nw_kernels2.cuh"
 #include "../../ninwavelets_b200/csrc/nw_plan.h"
 
+#include <ucontext.h>
+#include <functional>
+
 using namespace nw;
+
+// ---- a block of `nthr` emulated threads stepped as fibers; NW_SYNC() is a real barrier -----------
+// Every thread runs until its next barrier (or its end), round robin: a missing or misplaced
+// barrier shows up as a wrong result, exactly as thread 0 racing ahead would on the device.
+namespace {
+struct Fibers {
+    static const size_t STACK = 256 * 1024;
+    ucontext_t main_ctx;
+    std::vector<ucontext_t> ctx;
+    std::vector<char> done;
+    std::vector<char> stacks;
+    const std::function<void(int)>* body = nullptr;
+    int cur = 0;
+    static Fibers& get() { static Fibers f; return f; }
+    static void sync_hook() { Fibers& f = get(); swapcontext(&f.ctx[f.cur], &f.main_ctx); }
+    static void tramp() {
+        Fibers& f = get();
+        (*f.body)(f.cur);
+        f.done[f.cur] = 1;
+        swapcontext(&f.ctx[f.cur], &f.main_ctx);
+    }
+    void run(int nthr, const std::function<void(int)>& fn) {
+        if (nthr <= 1) { host_sync_hook() = nullptr; fn(0); return; }
+        body = &fn;
+        ctx.assign(nthr, ucontext_t());
+        done.assign(nthr, 0);
+        if (stacks.size() < (size_t)nthr * STACK) stacks.resize((size_t)nthr * STACK);
+        for (int t = 0; t < nthr; ++t) {
+            getcontext(&ctx[t]);
+            ctx[t].uc_stack.ss_sp = stacks.data() + (size_t)t * STACK;
+            ctx[t].uc_stack.ss_size = STACK;
+            ctx[t].uc_link = &main_ctx;
+            makecontext(&ctx[t], (void (*)())tramp, 0);
+        }
+        host_sync_hook() = sync_hook;
+        for (bool any = true; any;) {
+            any = false;
+            for (int t = 0; t < nthr; ++t)
+                if (!done[t]) { cur = t; swapcontext(&main_ctx, &ctx[t]); any = any || !done[t]; }
+        }
+        host_sync_hook() = nullptr;
+    }
+};
+int g_mode = 0;   // bit 1: generic kernels only; bit 2: one stepping thread per block (no fibers)
+}  // namespace
 
 template <typename T>
 static void fill_tw(std::vector<cx<T>>& v, long long count, long long P, long long step) {
@@ -81,6 +130,42 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
         P.Xout = X.data();
         for (int y = 0; y < gs; ++y) for (int x = 0; x < tilesA; ++x) passA_body<T, -1>(P, smem.data(), x, y, 0, 1);
         for (int y = 0; y < gs; ++y) for (int x = 0; x < tilesB; ++x) passB_body<T, -1>(P, smem.data(), x, y, 0, 1);
+        if (hp.fast && !(g_mode & 2)) {
+            std::vector<cx<T>> twA2, twB2;
+            fill_tw<T>(twA2, hp.N1f, hp.N1f, 1);
+            fill_tw<T>(twB2, hp.N2f, hp.N2f, 1);
+            Long2Params<T> Q;
+            memset(&Q, 0, sizeof(Q));
+            Q.N = hp.N; Q.N1 = hp.N1f; Q.N2 = hp.N2f; Q.F = hp.F; Q.tpshA = hp.tpshA; Q.tpshB = hp.tpshB;
+            Q.stA = hp.stA2; Q.stB = hp.stB2; Q.twA = twA2.data(); Q.twB = twB2.data(); Q.twH = twH.data(); Q.twL = twL.data();
+            Q.lb = hp.lb; Q.tm_stride = hp.tm_stride2; Q.sp = sp;
+            const int ring2 = hp.ring2 < 3 ? hp.ring2 : 3;
+            std::vector<cx<T>> Tm2((size_t)ring2 * hp.tm_stride2);
+            Q.X = X.data(); Q.Tm = Tm2.data();
+            Q.out = (char*)out + (size_t)s0 * hp.F * (size_t)hp.N * esz; Q.out_mode = output;
+            const int tA = (hp.N2f + (2 << hp.tpshA) - 1) / (2 << hp.tpshA), tB = (hp.N1f + (2 << hp.tpshB) - 1) / (2 << hp.tpshB);
+            std::vector<char> sm2(std::max(hp.smem_A2, hp.smem_B2) + 64);
+            char* smp = (char*)(((uintptr_t)sm2.data() + 31) & ~(uintptr_t)31);
+            const int ntA = (g_mode & 4) ? 1 : hp.nthrA2, ntB = (g_mode & 4) ? 1 : hp.nthrB2;
+            const long long rows = (long long)gs * hp.F;
+            for (long long r0 = 0; r0 < rows; r0 += ring2) {
+                const int g = (int)std::min<long long>(ring2, rows - r0);
+                Q.row0 = (int)r0;
+                for (int y = 0; y < g; ++y) for (int x = 0; x < tA; ++x)
+                    Fibers::get().run(ntA, [&](int t) { passA2_body<T>(Q, smp, x, y, t, ntA); });
+                for (int y = 0; y < g; ++y) for (int x = 0; x < tB; ++x)
+                    Fibers::get().run(ntB, [&](int t) {
+                        if (output == OUT_POWER) passB2_body<T, OUT_POWER>(Q, smp, x, y, t, ntB);
+                        else if (output == OUT_ABS) passB2_body<T, OUT_ABS>(Q, smp, x, y, t, ntB);
+                        else passB2_body<T, OUT_CWT>(Q, smp, x, y, t, ntB);
+                    });
+            }
+            if (bl != BL_NONE) {
+                double sh[2];
+                for (long long r = 0; r < rows; ++r) baseline_rows_body<T>((T*)Q.out, hp.N, bl, (int)blo, (int)bhi, sh, (int)r, 0, 1);
+            }
+            continue;
+        }
         for (int si = 0; si < gs; ++si) {
             P.X = X.data() + (size_t)si * hp.N;
             char* out_s = (char*)out + (size_t)(s0 + si) * hp.F * (size_t)hp.N * esz;
@@ -115,7 +200,8 @@ extern "C" int emul_transform(const nwcwt_plan_desc* d, const void* signals, voi
     plan_geometry(hp);
     plan_bands(hp);
     std::string err;
-    if (!plan_shape(hp, err, force_long != 0)) {
+    g_mode = force_long;
+    if (!plan_shape(hp, err, (force_long & 1) != 0)) {
         strncpy(errbuf, err.c_str(), errlen - 1);
         return -2;
     }

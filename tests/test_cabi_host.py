@@ -34,11 +34,11 @@ def test_short_and_long_shapes():
     i = plan(1500, np.arange(1, 101.0)).info()
     assert i["path"] == "short" and np.prod(i["radices"][0]) == 1500 and i["smem_bytes"] <= 227 * 1024
     i = plan(600000, np.arange(1, 101.0)).info()
-    assert i["path"] == "long" and i["n1"] * i["n2"] == 600000
+    assert i["path"] == "long_packed" and i["n1"] * i["n2"] == 600000
     assert np.prod(i["radices"][0]) == i["n1"] and np.prod(i["radices"][1]) == i["n2"]
     assert i["smem_bytes"] <= 227 * 1024
     i = plan(1 << 20, np.arange(1, 129.0), dtype=np.float64).info()
-    assert i["path"] == "long" and i["n1"] * i["n2"] == 1 << 20 and i["smem_bytes"] <= 227 * 1024
+    assert i["path"] == "long_packed" and i["n1"] * i["n2"] == 1 << 20 and i["smem_bytes"] <= 227 * 1024
     for e in (16, 18, 22):
         assert plan(1 << e, [1.0, 2.0]).info()["n1"] * plan(1 << e, [1.0, 2.0]).info()["n2"] == 1 << e
 
