@@ -58,27 +58,45 @@ template <typename T, int R> NW_HD void tw_powers(cx<T> w, cx<T>* p) {
 
 template <typename T, int DIR> NW_HD cx<T> tw_dir(cx<T> w) { return DIR > 0 ? w : mk<T>(w.x, -w.y); }
 
+// Geometry of one pass: P points, blocks of L = P / ns with Q = L / R butterflies each (= element
+// stride), twiddle table stride tws = ns, 2^tpsh lane pairs interleaved.  GeoDyn reads a run-time
+// plan; GeoStat is the same interface with everything a compile-time constant - used by the kernels
+// specialised for the hot lengths, where the element offsets become immediates of the LDS/STS and the
+// divisions fold away (about a third fewer instructions per butterfly than the run-time form).
+struct GeoDyn {
+    const Fft2Plan* st;
+    int s, P, L, Q, tws, tpsh;
+    NW_HD GeoDyn(const Fft2Plan& p, int stage, int tpsh_, int R) : st(&p), s(stage), P(p.P), L(p.P / p.ns[stage]),
+        Q(p.P / p.ns[stage] / R), tws(p.ns[stage]), tpsh(tpsh_) {}
+    NW_HD int blk_of(int bi) const { return (int)fd_div((uint32_t)bi, st->div_q[s]); }
+    NW_HD int rev(int blk) const { return fft2_rev(*st, blk); }
+};
+struct RevNone { static NW_HD int rev(int blk) { return blk; } };                    // <= 2 passes
+template <int R0, int R1> struct Rev3 {                                                // 3 passes: blk = k0 R1 + k1
+    static NW_HD int rev(int blk) { const int k0 = blk / R1; return k0 + R0 * (blk - k0 * R1); }
+};
+template <int PS, int NSS, int R, int TPS, class REV> struct GeoStat {
+    static constexpr int P = PS, L = PS / NSS, Q = PS / NSS / R, tws = NSS, tpsh = TPS;
+    NW_HD int blk_of(int bi) const { return bi / Q; }
+    NW_HD int rev(int blk) const { return REV::rev(blk); }
+};
+
 // ---- decimation in frequency ------------------------------------------------------------
-template <typename T, int R, int DIR, bool LAST, bool RAW, class Dst>
-NW_HD void dif_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
-                     const Dst& dst, int tid, int nthr) {
-    const int P = st.P;
-    const int L = P / st.ns[s];          // block length of this stage
-    const int Q = L / R;                 // butterflies per block = stride
-    const int tws = st.ns[s];            // P / L
-    const uint32_t nwork = (uint32_t)(P / R) << tpsh;
-    const int TP = 1 << tpsh;
+template <typename T, int R, int DIR, bool LAST, bool RAW, class G, class Dst>
+NW_HD void dif_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid, int nthr) {
+    const int tpsh = g.tpsh, TP = 1 << tpsh;
+    const uint32_t nwork = (uint32_t)(g.P / R) << tpsh;
 #pragma unroll 1
     for (uint32_t lin = tid; lin < nwork; lin += nthr) {
         const int tp = (int)(lin & (TP - 1));
         const int bi = (int)(lin >> tpsh);
-        const int blk = LAST ? bi : (int)fd_div((uint32_t)bi, st.div_q[s]);   // bi / Q
-        const int np = bi - blk * Q;
-        cx2<T>* e = buf + (((size_t)blk * L + np) << tpsh) + tp;
-        const size_t stride = (size_t)Q << tpsh;
+        const int blk = LAST ? bi : g.blk_of(bi);   // bi / Q
+        const int np = bi - blk * g.Q;
+        cx2<T>* e = buf + (((size_t)blk * g.L + np) << tpsh) + tp;
+        const int stride = g.Q << tpsh;
         cx2<T> v[R];
         typename Dst::Ctx ctx;
-        if (LAST) ctx = dst.begin(fft2_rev(st, blk), P / R, tp);   // issues the epilogue's own loads early
+        if (LAST) ctx = dst.begin(g.rev(blk), g.P / R, tp);   // issues the epilogue's own loads early
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = RAW ? raw_to_packed<T>(e[r * stride]) : e[r * stride];
         B2<T, R, DIR>::run(v);
@@ -86,12 +104,18 @@ NW_HD void dif_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRI
             dst.template store_all<R>(ctx, v);
         } else {
             cx<T> w[R];
-            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * tws]), w);
+            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * g.tws]), w);
             e[0] = v[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) e[r * stride] = cmul_s(v[r], w[r]);
         }
     }
+}
+
+template <typename T, int R, int DIR, bool LAST, bool RAW, class Dst>
+NW_HD void dif_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
+                     const Dst& dst, int tid, int nthr) {
+    dif_body<T, R, DIR, LAST, RAW>(GeoDyn(st, s, tpsh, R), tw, buf, dst, tid, nthr);
 }
 
 template <typename T, int DIR, bool LAST, bool RAW, class Dst>
@@ -132,6 +156,20 @@ NW_HD void fft2_dif(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, c
     dif_stage_any<T, DIR, true, false>(st, st.nst - 1, tpsh, tw, buf, dst, tid, nthr);
 }
 
+// The same transform for a compile-time plan P = R0 R1 R2 (R2 = 1: two passes).
+template <typename T, int DIR, bool RAW0, int TPS, int P, int R0, int R1, int R2, class Dst>
+NW_HD void fft2_dif_static(const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid, int nthr) {
+    dif_body<T, R0, DIR, false, RAW0>(GeoStat<P, 1, R0, TPS, RevNone>(), tw, buf, dst, tid, nthr);
+    NW_SYNC();
+    if (R2 > 1) {
+        dif_body<T, R1, DIR, false, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, dst, tid, nthr);
+        NW_SYNC();
+        dif_body<T, (R2 > 1 ? R2 : 2), DIR, true, false>(GeoStat<P, R0 * R1, (R2 > 1 ? R2 : 2), TPS, Rev3<R0, R1>>(), tw, buf, dst, tid, nthr);
+    } else {
+        dif_body<T, R1, DIR, true, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, dst, tid, nthr);
+    }
+}
+
 // Src tag: the input already sits in buf at its decimation-in-time position (fft2_dit_pos)
 struct FromBuf {};
 template <class S> struct is_from_buf { static const bool value = false; };
@@ -154,36 +192,32 @@ NW_HD int fft2_dit_pos(const Fft2Plan& st, int n) {
 // ---- decimation in time ---------------------------------------------------------------------
 // pass index q = 0 runs radix[nst-1] on contiguous groups, reading from Src at digit-reversed
 // indices; the last pass runs radix[0] at stride P / R_0 and writes natural-order results to Dst.
-template <typename T, int R, int DIR, bool FIRST, bool LAST, class Src, class Dst>
-NW_HD void dit_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
-                     const Dst& dst, int tid, int nthr) {
-    const int P = st.P;
-    const int L = P / st.ns[s];
-    const int Q = L / R;
-    const int tws = st.ns[s];
-    const uint32_t nwork = (uint32_t)(P / R) << tpsh;
-    const int TP = 1 << tpsh;
+template <typename T, int R, int DIR, bool FIRST, bool LAST, class G, class Src, class Dst>
+NW_HD void dit_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src, const Dst& dst, int tid,
+                    int nthr) {
+    const int tpsh = g.tpsh, TP = 1 << tpsh;
+    const uint32_t nwork = (uint32_t)(g.P / R) << tpsh;
 #pragma unroll 1
     for (uint32_t lin = tid; lin < nwork; lin += nthr) {
         const int tp = (int)(lin & (TP - 1));
         const int bi = (int)(lin >> tpsh);
-        const int blk = FIRST ? bi : (int)fd_div((uint32_t)bi, st.div_q[s]);
-        const int np = bi - blk * Q;
-        cx2<T>* e = buf + (((size_t)blk * L + np) << tpsh) + tp;
-        const size_t stride = (size_t)Q << tpsh;
+        const int blk = FIRST ? bi : g.blk_of(bi);
+        const int np = bi - blk * g.Q;
+        cx2<T>* e = buf + (((size_t)blk * g.L + np) << tpsh) + tp;
+        const int stride = g.Q << tpsh;
         cx2<T> v[R];
         typename Dst::Ctx ctx;
-        if (LAST) ctx = dst.begin(np, Q, tp);   // blk == 0, L == P; issues the epilogue's own loads early
+        if (LAST) ctx = dst.begin(np, g.Q, tp);   // blk == 0, L == P; issues the epilogue's own loads early
         if (FIRST) {
             if constexpr (is_from_buf<Src>::value) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) v[r] = e[r * stride];
             } else {
-                src.template load_all<R>(fft2_rev(st, blk), P / R, tp, v);
+                src.template load_all<R>(g.rev(blk), g.P / R, tp, v);
             }
         } else {
             cx<T> w[R];
-            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * tws]), w);
+            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * g.tws]), w);
             v[0] = e[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = cmul_s(e[r * stride], w[r]);
@@ -196,6 +230,12 @@ NW_HD void dit_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRI
             for (int r = 0; r < R; ++r) e[r * stride] = v[r];
         }
     }
+}
+
+template <typename T, int R, int DIR, bool FIRST, bool LAST, class Src, class Dst>
+NW_HD void dit_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
+                     const Dst& dst, int tid, int nthr) {
+    dit_body<T, R, DIR, FIRST, LAST>(GeoDyn(st, s, tpsh, R), tw, buf, src, dst, tid, nthr);
 }
 
 template <typename T, int DIR, bool FIRST, bool LAST, class Src, class Dst>
@@ -232,6 +272,22 @@ NW_HD void fft2_dit(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, c
         NW_SYNC();
     }
     dit_stage_any<T, DIR, false, true>(st, 0, tpsh, tw, buf, src, dst, tid, nthr);
+}
+
+// Compile-time plan P = R0 R1 R2 (radix order as in Fft2Plan: the first pass runs the LAST radix; R2 = 1:
+// two passes).  Input already in buf at its fft2_dit_pos slots.
+template <typename T, int DIR, int TPS, int P, int R0, int R1, int R2, class Dst>
+NW_HD void fft2_dit_static(const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid, int nthr) {
+    const FromBuf src;
+    if (R2 > 1) {
+        dit_body<T, (R2 > 1 ? R2 : 2), DIR, true, false>(GeoStat<P, R0 * R1, (R2 > 1 ? R2 : 2), TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
+        NW_SYNC();
+        dit_body<T, R1, DIR, false, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
+    } else {
+        dit_body<T, R1, DIR, true, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
+    }
+    NW_SYNC();
+    dit_body<T, R0, DIR, false, true>(GeoStat<P, 1, R0, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
 }
 
 }  // namespace nw

@@ -1,7 +1,15 @@
-// Fast long-row kernels (packed in-place engine; nw_kernels2.cuh), instantiated for NW_REAL and
-// the launch shapes NW_CFG_LIST (nw_plan.h: CFG2_MAXTHR / CFG2_MINCTA give the register budget).
+// Fast long-row kernels (packed in-place engine; nw_kernels2.cuh), instantiated for NW_REAL, one launch
+// shape NW_CFG (nw_plan.h: CFG2_*) and the compile-time plans listed in NW_SP_A / NW_SP_B (X-macro lists of
+// StaticPlan ids; the run-time plan, id 0, is always there).
 #include "nw_launch.h"
 #include "nw_plan.h"
+
+#ifndef NW_SP_A
+#define NW_SP_A(X)
+#endif
+#ifndef NW_SP_B
+#define NW_SP_B(X)
+#endif
 
 namespace nw {
 template <int CFG> struct Cfg2;
@@ -11,46 +19,67 @@ template <> struct Cfg2<1> { static const int maxreg = 96; };               // 2
 template <> struct Cfg2<2> { static const int maxreg = 96; };               // 128 x 5
 template <> struct Cfg2<3> { static const int maxreg = 128; };              //  64 x 8
 
-template <typename T, int CFG>
+template <typename T, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2_kernel(const __grid_constant__ Long2Params<T> P) {
     extern __shared__ __align__(32) char nw_smem[];
-    passA2_body<T>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+    passA2_body<T, SP>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
-template <typename T, int MODE, int CFG>
+template <typename T, int MODE, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passB2_kernel(const __grid_constant__ Long2Params<T> P) {
     extern __shared__ __align__(32) char nw_smem[];
-    passB2_body<T, MODE>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+    passB2_body<T, MODE, SP>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
 
-template <typename T, int CFG> static cudaError_t prepare_cfg() {
+template <typename T, int CFG, int SP> static cudaError_t prepA() {
+    return cudaFuncSetAttribute(nwcwt_passA2_kernel<T, CFG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+}
+template <typename T, int CFG, int SP> static cudaError_t prepB() {
     const int v = (int)SMEM_MAX;
-    cudaError_t e = cudaFuncSetAttribute(nwcwt_passA2_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+    cudaError_t e = cudaFuncSetAttribute(nwcwt_passB2_kernel<T, OUT_CWT, CFG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(nwcwt_passB2_kernel<T, OUT_CWT, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+    e = cudaFuncSetAttribute(nwcwt_passB2_kernel<T, OUT_ABS, CFG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(nwcwt_passB2_kernel<T, OUT_ABS, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(nwcwt_passB2_kernel<T, OUT_POWER, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+    return cudaFuncSetAttribute(nwcwt_passB2_kernel<T, OUT_POWER, CFG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
 }
-template <typename T, int CFG> static cudaError_t launchA_cfg(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
-    nwcwt_passA2_kernel<T, CFG><<<grid, nthr, smem, s>>>(P);
+template <typename T, int CFG, int SP> static cudaError_t runA(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
+    nwcwt_passA2_kernel<T, CFG, SP><<<grid, nthr, smem, s>>>(P);
     return cudaGetLastError();
 }
-template <typename T, int CFG> static cudaError_t launchB_cfg(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
-    if (P.out_mode == OUT_POWER) nwcwt_passB2_kernel<T, OUT_POWER, CFG><<<grid, nthr, smem, s>>>(P);
-    else if (P.out_mode == OUT_ABS) nwcwt_passB2_kernel<T, OUT_ABS, CFG><<<grid, nthr, smem, s>>>(P);
-    else nwcwt_passB2_kernel<T, OUT_CWT, CFG><<<grid, nthr, smem, s>>>(P);
+template <typename T, int CFG, int SP> static cudaError_t runB(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
+    if (P.out_mode == OUT_POWER) nwcwt_passB2_kernel<T, OUT_POWER, CFG, SP><<<grid, nthr, smem, s>>>(P);
+    else if (P.out_mode == OUT_ABS) nwcwt_passB2_kernel<T, OUT_ABS, CFG, SP><<<grid, nthr, smem, s>>>(P);
+    else nwcwt_passB2_kernel<T, OUT_CWT, CFG, SP><<<grid, nthr, smem, s>>>(P);
     return cudaGetLastError();
 }
 
-#define NW_CFG_CASE(c, call) case c: return call
-template <> cudaError_t prepare_long2<NW_REAL, NW_CFG>() { return prepare_cfg<NW_REAL, NW_CFG>(); }
-template <>
-cudaError_t launch_passA2<NW_REAL, NW_CFG>(const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
-    return launchA_cfg<NW_REAL, NW_CFG>(P, grid, nthr, smem, s);
+#define NW_PREP_A(id) { cudaError_t e = prepA<NW_REAL, NW_CFG, id>(); if (e != cudaSuccess) return e; }
+#define NW_PREP_B(id) { cudaError_t e = prepB<NW_REAL, NW_CFG, id>(); if (e != cudaSuccess) return e; }
+#define NW_HAS(id) if (sp == id) return true;
+#define NW_RUN_A(id) case id: return runA<NW_REAL, NW_CFG, id>(P, grid, nthr, smem, s);
+#define NW_RUN_B(id) case id: return runB<NW_REAL, NW_CFG, id>(P, grid, nthr, smem, s);
+
+template <> cudaError_t prepare_long2<NW_REAL, NW_CFG>() {
+    NW_PREP_A(0) NW_SP_A(NW_PREP_A)
+    NW_PREP_B(0) NW_SP_B(NW_PREP_B)
+    return cudaSuccess;
+}
+template <> bool has_static_plan<NW_REAL, NW_CFG>(int pass, int sp) {
+    if (sp == 0) return true;
+    if (pass == 0) { NW_SP_A(NW_HAS) } else { NW_SP_B(NW_HAS) }
+    return false;
 }
 template <>
-cudaError_t launch_passB2<NW_REAL, NW_CFG>(const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
-    return launchB_cfg<NW_REAL, NW_CFG>(P, grid, nthr, smem, s);
+cudaError_t launch_passA2<NW_REAL, NW_CFG>(int sp, const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
+    switch (sp) {
+        NW_SP_A(NW_RUN_A)
+        default: return runA<NW_REAL, NW_CFG, 0>(P, grid, nthr, smem, s);
+    }
+}
+template <>
+cudaError_t launch_passB2<NW_REAL, NW_CFG>(int sp, const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
+    switch (sp) {
+        NW_SP_B(NW_RUN_B)
+        default: return runB<NW_REAL, NW_CFG, 0>(P, grid, nthr, smem, s);
+    }
 }
 }  // namespace nw

@@ -39,6 +39,30 @@ struct Long2Params {
     SpecParams<T> sp;
 };
 
+// Compile-time plans of the hot lengths (nw_fft2.cuh: fft2_dif_static / fft2_dit_static).  0 = run-time plan.
+template <int ID> struct StaticPlan { static const int P = 0, R0 = 1, R1 = 1, R2 = 1, TPS = 0; };
+template <> struct StaticPlan<1> { static const int P = 1000, R0 = 10, R1 = 10, R2 = 10, TPS = 2; };
+template <> struct StaticPlan<2> { static const int P = 600, R0 = 12, R1 = 10, R2 = 5, TPS = 2; };
+template <> struct StaticPlan<3> { static const int P = 1024, R0 = 16, R1 = 16, R2 = 4, TPS = 2; };
+template <> struct StaticPlan<4> { static const int P = 256, R0 = 16, R1 = 16, R2 = 1, TPS = 2; };
+template <> struct StaticPlan<5> { static const int P = 512, R0 = 16, R1 = 8, R2 = 4, TPS = 2; };
+static const int N_STATIC_PLANS = 5;
+template <int ID> NW_HD bool static_plan_matches(const Fft2Plan& st, int tpsh) {
+    typedef StaticPlan<ID> S;
+    if (st.P != S::P || tpsh != S::TPS) return false;
+    const int n = S::R2 > 1 ? 3 : 2;
+    if (st.nst != n || st.radix[0] != S::R0 || st.radix[1] != S::R1) return false;
+    return n == 2 || st.radix[2] == S::R2;
+}
+inline int static_plan_id(const Fft2Plan& st, int tpsh) {
+    if (static_plan_matches<1>(st, tpsh)) return 1;
+    if (static_plan_matches<2>(st, tpsh)) return 2;
+    if (static_plan_matches<3>(st, tpsh)) return 3;
+    if (static_plan_matches<4>(st, tpsh)) return 4;
+    if (static_plan_matches<5>(st, tpsh)) return 5;
+    return 0;
+}
+
 template <typename T> NW_HD cx<T> big_twiddle2(const Long2Params<T>& P, int m) {
     const cx<T> a = P.twH[m >> P.lb];
     const cx<T> b = P.twL[m & ((1 << P.lb) - 1)];
@@ -96,7 +120,7 @@ template <typename T> NW_HD size_t passB2_smem_bytes(int N2, int tpsh) { return 
 // The tile's input - spectrum x signal spectrum on the non-zero band only - is gathered into the
 // transform's shared-memory slots by a compact loop (one evaluation per in-band bin, nothing unrolled
 // around the formula), the rest of the tile is zero.
-template <typename T>
+template <typename T, int SP>
 NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
     cx2<T>* buf = (cx2<T>*)smem;
     const int tpsh = P.tpshA, TP = 1 << tpsh;
@@ -127,7 +151,9 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     }
     NW_SYNC();
     TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c};
-    fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
+    typedef StaticPlan<SP> S;
+    if (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
+    else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twA, buf, dst, tid, nthr);
 }
 
 // ---- pass B --------------------------------------------------------------------------------
@@ -183,7 +209,7 @@ template <typename T, int MODE> struct LongOutDst2 {
     }
 };
 
-template <typename T, int MODE>
+template <typename T, int MODE, int SP>
 NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
     const int shB = P.tpshB + 1;
     const int TB = 1 << shB;
@@ -211,7 +237,9 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const int gr = P.row0 + by;
     const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
     LongOutDst2<T, MODE> dst{(char*)P.out + (size_t)gr * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
-    fft2_dif<T, +1, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
+    typedef StaticPlan<SP> S;
+    if (SP == 0) fft2_dif<T, +1, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
+    else fft2_dif_static<T, +1, true, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
 }
 
 }  // namespace nw

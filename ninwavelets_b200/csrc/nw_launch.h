@@ -16,10 +16,12 @@ template <typename T>
 cudaError_t launch_passA(int dir, const LongParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
 template <typename T>
 cudaError_t launch_passB(int dir, const LongParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
-// fast long-row path (nw_kernels2.cuh); CFG = compiled launch shape (nw_plan.h CFG2_*)
+// fast long-row path (nw_kernels2.cuh); CFG = compiled launch shape (nw_plan.h CFG2_*), sp = StaticPlan id
+// (0 = run-time plan); has_static_plan says whether the (pass, sp) kernel exists in shape CFG (pass 0 = A, 1 = B)
 template <typename T, int CFG> cudaError_t prepare_long2();
+template <typename T, int CFG> bool has_static_plan(int pass, int sp);
 template <typename T, int CFG>
-cudaError_t launch_passA2(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+cudaError_t launch_passA2(int sp, const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
 template <typename T, int CFG>
-cudaError_t launch_passB2(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+cudaError_t launch_passB2(int sp, const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
 }  // namespace nw

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) nwcwt_reduce_kernel(const void* in, T* ou
 // plan object
 // ---------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static bool g_no_static = getenv("NWCWT_NO_STATIC") != nullptr;   // tuning: run-time plans only
 static bool g_force_generic = false;   // nwcwt_debug_force_generic: run the generic kernels even where a fast path exists
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -154,41 +155,35 @@ static void fill_twiddles(std::vector<cx<T>>& v, long long count, long long P, l
     }
 }
 
-// fast long path: compiled launch shapes per precision (k_long2_*.cu)
+// fast long path: compiled launch shapes and compile-time plans per precision (k_long2_*.cu)
 template <typename T> struct Long2Dispatch;
+#define NW_BY_CFG(c, expr0, expr1, expr2, expr3) \
+    switch (c) { case 1: return expr1; case 2: return expr2; case 3: return expr3; default: return expr0; }
 template <> struct Long2Dispatch<float> {
     static cudaError_t prepare(int c) {
-        switch (c) {
-            case 1: return prepare_long2<float, 1>();
-            case 2: return prepare_long2<float, 2>();
-            case 3: return prepare_long2<float, 3>();
-            default: return prepare_long2<float, 0>();
-        }
+        NW_BY_CFG(c, (prepare_long2<float, 0>()), (prepare_long2<float, 1>()), (prepare_long2<float, 2>()), (prepare_long2<float, 3>()))
     }
-    static cudaError_t A(int c, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
-        switch (c) {
-            case 1: return launch_passA2<float, 1>(P, g, nt, sm, s);
-            case 2: return launch_passA2<float, 2>(P, g, nt, sm, s);
-            case 3: return launch_passA2<float, 3>(P, g, nt, sm, s);
-            default: return launch_passA2<float, 0>(P, g, nt, sm, s);
-        }
+    static bool has(int c, int pass, int sp) {
+        NW_BY_CFG(c, (has_static_plan<float, 0>(pass, sp)), (has_static_plan<float, 1>(pass, sp)),
+                  (has_static_plan<float, 2>(pass, sp)), (has_static_plan<float, 3>(pass, sp)))
     }
-    static cudaError_t B(int c, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
-        switch (c) {
-            case 1: return launch_passB2<float, 1>(P, g, nt, sm, s);
-            case 2: return launch_passB2<float, 2>(P, g, nt, sm, s);
-            case 3: return launch_passB2<float, 3>(P, g, nt, sm, s);
-            default: return launch_passB2<float, 0>(P, g, nt, sm, s);
-        }
+    static cudaError_t A(int c, int sp, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        NW_BY_CFG(c, (launch_passA2<float, 0>(sp, P, g, nt, sm, s)), (launch_passA2<float, 1>(sp, P, g, nt, sm, s)),
+                  (launch_passA2<float, 2>(sp, P, g, nt, sm, s)), (launch_passA2<float, 3>(sp, P, g, nt, sm, s)))
+    }
+    static cudaError_t B(int c, int sp, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        NW_BY_CFG(c, (launch_passB2<float, 0>(sp, P, g, nt, sm, s)), (launch_passB2<float, 1>(sp, P, g, nt, sm, s)),
+                  (launch_passB2<float, 2>(sp, P, g, nt, sm, s)), (launch_passB2<float, 3>(sp, P, g, nt, sm, s)))
     }
 };
 template <> struct Long2Dispatch<double> {
     static cudaError_t prepare(int) { return prepare_long2<double, 0>(); }
-    static cudaError_t A(int, const Long2Params<double>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
-        return launch_passA2<double, 0>(P, g, nt, sm, s);
+    static bool has(int, int pass, int sp) { return has_static_plan<double, 0>(pass, sp); }
+    static cudaError_t A(int, int sp, const Long2Params<double>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        return launch_passA2<double, 0>(sp, P, g, nt, sm, s);
     }
-    static cudaError_t B(int, const Long2Params<double>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
-        return launch_passB2<double, 0>(P, g, nt, sm, s);
+    static cudaError_t B(int, int sp, const Long2Params<double>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
+        return launch_passB2<double, 0>(sp, P, g, nt, sm, s);
     }
 };
 
@@ -419,6 +414,10 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
             const unsigned tB = (unsigned)((hp.N1f + (2 << hp.tpshB) - 1) / (2 << hp.tpshB));
             const long long rows = (long long)gs * hp.F;
             const int ns = pl->n_aux;
+            // kernels specialised for this plan at compile time, where the library has them
+            int spA = g_no_static ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = g_no_static ? 0 : static_plan_id(hp.stB2, hp.tpshB);
+            if (!Long2Dispatch<T>::has(hp.cfgA, 0, spA)) spA = 0;
+            if (!Long2Dispatch<T>::has(hp.cfgB, 1, spB)) spB = 0;
             if (ns > 1) {
                 CUDA_TRY(cudaEventRecord(pl->ev_fork, stream));
                 for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(pl->aux[i], pl->ev_fork, 0));
@@ -430,8 +429,8 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
                 cudaStream_t st = ns > 1 ? pl->aux[slot] : stream;
                 Q.row0 = (int)r0;
                 Q.Tm = Tm + (size_t)slot * (size_t)hp.ring2 * (size_t)hp.tm_stride2;
-                { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, Q, dim3(tA, g), hp.nthrA2, hp.smem_A2, st)); }
-                { LaunchScope ls(4, st); CUDA_TRY(Long2Dispatch<T>::B(hp.cfgB, Q, dim3(tB, g), hp.nthrB2, hp.smem_B2, st)); }
+                { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, spA, Q, dim3(tA, g), hp.nthrA2, hp.smem_A2, st)); }
+                { LaunchScope ls(4, st); CUDA_TRY(Long2Dispatch<T>::B(hp.cfgB, spB, Q, dim3(tB, g), hp.nthrB2, hp.smem_B2, st)); }
             }
             if (ns > 1)
                 for (int i = 0; i < ns; ++i) {

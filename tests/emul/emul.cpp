@@ -148,16 +148,23 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
             char* smp = (char*)(((uintptr_t)sm2.data() + 31) & ~(uintptr_t)31);
             const int ntA = (g_mode & 4) ? 1 : hp.nthrA2, ntB = (g_mode & 4) ? 1 : hp.nthrB2;
             const long long rows = (long long)gs * hp.F;
+            const int spA = (g_mode & 8) ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = (g_mode & 8) ? 0 : static_plan_id(hp.stB2, hp.tpshB);
             for (long long r0 = 0; r0 < rows; r0 += ring2) {
                 const int g = (int)std::min<long long>(ring2, rows - r0);
                 Q.row0 = (int)r0;
                 for (int y = 0; y < g; ++y) for (int x = 0; x < tA; ++x)
-                    Fibers::get().run(ntA, [&](int t) { passA2_body<T>(Q, smp, x, y, t, ntA); });
+                    Fibers::get().run(ntA, [&](int t) {
+                        switch (spA) {
+                            case 2: passA2_body<T, 2>(Q, smp, x, y, t, ntA); break;
+                            case 4: passA2_body<T, 4>(Q, smp, x, y, t, ntA); break;
+                            default: passA2_body<T, 0>(Q, smp, x, y, t, ntA); break;
+                        }
+                    });
                 for (int y = 0; y < g; ++y) for (int x = 0; x < tB; ++x)
                     Fibers::get().run(ntB, [&](int t) {
-                        if (output == OUT_POWER) passB2_body<T, OUT_POWER>(Q, smp, x, y, t, ntB);
-                        else if (output == OUT_ABS) passB2_body<T, OUT_ABS>(Q, smp, x, y, t, ntB);
-                        else passB2_body<T, OUT_CWT>(Q, smp, x, y, t, ntB);
+                        if (output == OUT_POWER) { if (spB == 1) passB2_body<T, OUT_POWER, 1>(Q, smp, x, y, t, ntB); else if (spB == 4) passB2_body<T, OUT_POWER, 4>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_POWER, 0>(Q, smp, x, y, t, ntB); }
+                        else if (output == OUT_ABS) passB2_body<T, OUT_ABS, 0>(Q, smp, x, y, t, ntB);
+                        else { if (spB == 1) passB2_body<T, OUT_CWT, 1>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_CWT, 0>(Q, smp, x, y, t, ntB); }
                     });
             }
             if (bl != BL_NONE) {
