@@ -63,11 +63,27 @@ template <typename T, int DIR> NW_HD cx<T> tw_dir(cx<T> w) { return DIR > 0 ? w 
 // plan; GeoStat is the same interface with everything a compile-time constant - used by the kernels
 // specialised for the hot lengths, where the element offsets become immediates of the LDS/STS and the
 // divisions fold away (about a third fewer instructions per butterfly than the run-time form).
+// How many lane-pair sequences are interleaved in the buffer: 2^tpsh (tpsh >= 0), or any count with an
+// exact-division helper (tpsh < 0; pruned transforms interleave columns x phases).  twscale multiplies the
+// twiddle-table index: a length-P transform can use the table of any multiple of P.
+struct SeqDesc {
+    int tpsh, nseq, twscale;
+    fastdiv d;
+};
+NW_HD SeqDesc seq_pow2(int tpsh) { SeqDesc q; q.tpsh = tpsh; q.nseq = 1 << tpsh; q.twscale = 1; q.d.d = 1; q.d.m = 0; return q; }
+inline SeqDesc seq_any(int nseq, int twscale) { SeqDesc q; q.tpsh = -1; q.nseq = nseq; q.twscale = twscale; q.d = make_fastdiv((uint32_t)nseq); return q; }
+
 struct GeoDyn {
     const Fft2Plan* st;
-    int s, P, L, Q, tws, tpsh;
-    NW_HD GeoDyn(const Fft2Plan& p, int stage, int tpsh_, int R) : st(&p), s(stage), P(p.P), L(p.P / p.ns[stage]),
-        Q(p.P / p.ns[stage] / R), tws(p.ns[stage]), tpsh(tpsh_) {}
+    int s, P, L, Q, tws;
+    SeqDesc sq;
+    NW_HD GeoDyn(const Fft2Plan& p, int stage, const SeqDesc& q, int R) : st(&p), s(stage), P(p.P), L(p.P / p.ns[stage]),
+        Q(p.P / p.ns[stage] / R), tws(p.ns[stage] * q.twscale), sq(q) {}
+    NW_HD int nseq() const { return sq.nseq; }
+    NW_HD void split(uint32_t lin, int& t, int& bi) const {
+        if (sq.tpsh >= 0) { t = (int)(lin & (uint32_t)(sq.nseq - 1)); bi = (int)(lin >> sq.tpsh); }
+        else { bi = (int)fd_div(lin, sq.d); t = (int)lin - bi * sq.nseq; }
+    }
     NW_HD int blk_of(int bi) const { return (int)fd_div((uint32_t)bi, st->div_q[s]); }
     NW_HD int rev(int blk) const { return fft2_rev(*st, blk); }
 };
@@ -77,6 +93,8 @@ template <int R0, int R1> struct Rev3 {                                         
 };
 template <int PS, int NSS, int R, int TPS, class REV> struct GeoStat {
     static constexpr int P = PS, L = PS / NSS, Q = PS / NSS / R, tws = NSS, tpsh = TPS;
+    NW_HD constexpr int nseq() const { return 1 << TPS; }
+    NW_HD void split(uint32_t lin, int& t, int& bi) const { t = (int)(lin & ((1u << TPS) - 1u)); bi = (int)(lin >> TPS); }
     NW_HD int blk_of(int bi) const { return bi / Q; }
     NW_HD int rev(int blk) const { return REV::rev(blk); }
 };
@@ -84,16 +102,16 @@ template <int PS, int NSS, int R, int TPS, class REV> struct GeoStat {
 // ---- decimation in frequency ------------------------------------------------------------
 template <typename T, int R, int DIR, bool LAST, bool RAW, class G, class Dst>
 NW_HD void dif_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid, int nthr) {
-    const int tpsh = g.tpsh, TP = 1 << tpsh;
-    const uint32_t nwork = (uint32_t)(g.P / R) << tpsh;
+    const int nseq = g.nseq();
+    const uint32_t nwork = (uint32_t)(g.P / R) * (uint32_t)nseq;
 #pragma unroll 1
     for (uint32_t lin = tid; lin < nwork; lin += nthr) {
-        const int tp = (int)(lin & (TP - 1));
-        const int bi = (int)(lin >> tpsh);
+        int tp, bi;
+        g.split(lin, tp, bi);
         const int blk = LAST ? bi : g.blk_of(bi);   // bi / Q
         const int np = bi - blk * g.Q;
-        cx2<T>* e = buf + (((size_t)blk * g.L + np) << tpsh) + tp;
-        const int stride = g.Q << tpsh;
+        cx2<T>* e = buf + ((size_t)blk * g.L + np) * nseq + tp;
+        const int stride = g.Q * nseq;
         cx2<T> v[R];
         typename Dst::Ctx ctx;
         if (LAST) ctx = dst.begin(g.rev(blk), g.P / R, tp);   // issues the epilogue's own loads early
@@ -113,13 +131,13 @@ NW_HD void dif_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
 }
 
 template <typename T, int R, int DIR, bool LAST, bool RAW, class Dst>
-NW_HD void dif_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
+NW_HD void dif_stage(const Fft2Plan& st, int s, const SeqDesc& tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
                      const Dst& dst, int tid, int nthr) {
     dif_body<T, R, DIR, LAST, RAW>(GeoDyn(st, s, tpsh, R), tw, buf, dst, tid, nthr);
 }
 
 template <typename T, int DIR, bool LAST, bool RAW, class Dst>
-NW_HD void dif_stage_any(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
+NW_HD void dif_stage_any(const Fft2Plan& st, int s, const SeqDesc& tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
                          const Dst& dst, int tid, int nthr) {
     switch (st.radix[s]) {
         case 2: dif_stage<T, 2, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
@@ -140,8 +158,9 @@ NW_HD void dif_stage_any(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RE
 // RAW0: the units of buf are two plain complex values {re0, im0, re1, im1} (a tile as it sits in
 // global memory) instead of lane-packed {re0, re1, im0, im1}; the first pass repacks in registers.
 template <typename T, int DIR, bool RAW0, class Dst>
-NW_HD void fft2_dif(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid,
+NW_HD void fft2_dif(const Fft2Plan& st, int tpsh_, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid,
                     int nthr) {
+    const SeqDesc tpsh = seq_pow2(tpsh_);
     if (st.nst == 1) {
         dif_stage_any<T, DIR, true, RAW0>(st, 0, tpsh, tw, buf, dst, tid, nthr);
         return;
@@ -195,16 +214,16 @@ NW_HD int fft2_dit_pos(const Fft2Plan& st, int n) {
 template <typename T, int R, int DIR, bool FIRST, bool LAST, class G, class Src, class Dst>
 NW_HD void dit_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src, const Dst& dst, int tid,
                     int nthr) {
-    const int tpsh = g.tpsh, TP = 1 << tpsh;
-    const uint32_t nwork = (uint32_t)(g.P / R) << tpsh;
+    const int nseq = g.nseq();
+    const uint32_t nwork = (uint32_t)(g.P / R) * (uint32_t)nseq;
 #pragma unroll 1
     for (uint32_t lin = tid; lin < nwork; lin += nthr) {
-        const int tp = (int)(lin & (TP - 1));
-        const int bi = (int)(lin >> tpsh);
+        int tp, bi;
+        g.split(lin, tp, bi);
         const int blk = FIRST ? bi : g.blk_of(bi);
         const int np = bi - blk * g.Q;
-        cx2<T>* e = buf + (((size_t)blk * g.L + np) << tpsh) + tp;
-        const int stride = g.Q << tpsh;
+        cx2<T>* e = buf + ((size_t)blk * g.L + np) * nseq + tp;
+        const int stride = g.Q * nseq;
         cx2<T> v[R];
         typename Dst::Ctx ctx;
         if (LAST) ctx = dst.begin(np, g.Q, tp);   // blk == 0, L == P; issues the epilogue's own loads early
@@ -233,13 +252,13 @@ NW_HD void dit_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
 }
 
 template <typename T, int R, int DIR, bool FIRST, bool LAST, class Src, class Dst>
-NW_HD void dit_stage(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
+NW_HD void dit_stage(const Fft2Plan& st, int s, const SeqDesc& tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
                      const Dst& dst, int tid, int nthr) {
     dit_body<T, R, DIR, FIRST, LAST>(GeoDyn(st, s, tpsh, R), tw, buf, src, dst, tid, nthr);
 }
 
 template <typename T, int DIR, bool FIRST, bool LAST, class Src, class Dst>
-NW_HD void dit_stage_any(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
+NW_HD void dit_stage_any(const Fft2Plan& st, int s, const SeqDesc& tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf,
                          const Src& src, const Dst& dst, int tid, int nthr) {
     switch (st.radix[s]) {
         case 2: dit_stage<T, 2, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
@@ -258,20 +277,26 @@ NW_HD void dit_stage_any(const Fft2Plan& st, int s, int tpsh, const cx<T>* NW_RE
 
 // No barrier on entry or exit: the caller orders buf's reuse and dst's visibility.
 template <typename T, int DIR, class Src, class Dst>
-NW_HD void fft2_dit(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
+NW_HD void fft2_dit(const Fft2Plan& st, const SeqDesc& sq, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
                     const Dst& dst, int tid, int nthr) {
     const int m = st.nst;
     if (m == 1) {
-        dit_stage_any<T, DIR, true, true>(st, 0, tpsh, tw, buf, src, dst, tid, nthr);
+        dit_stage_any<T, DIR, true, true>(st, 0, sq, tw, buf, src, dst, tid, nthr);
         return;
     }
-    dit_stage_any<T, DIR, true, false>(st, m - 1, tpsh, tw, buf, src, dst, tid, nthr);
+    dit_stage_any<T, DIR, true, false>(st, m - 1, sq, tw, buf, src, dst, tid, nthr);
     NW_SYNC();
+#pragma unroll 1
     for (int s = m - 2; s >= 1; --s) {
-        dit_stage_any<T, DIR, false, false>(st, s, tpsh, tw, buf, src, dst, tid, nthr);
+        dit_stage_any<T, DIR, false, false>(st, s, sq, tw, buf, src, dst, tid, nthr);
         NW_SYNC();
     }
-    dit_stage_any<T, DIR, false, true>(st, 0, tpsh, tw, buf, src, dst, tid, nthr);
+    dit_stage_any<T, DIR, false, true>(st, 0, sq, tw, buf, src, dst, tid, nthr);
+}
+template <typename T, int DIR, class Src, class Dst>
+NW_HD void fft2_dit(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
+                    const Dst& dst, int tid, int nthr) {
+    fft2_dit<T, DIR>(st, seq_pow2(tpsh), tw, buf, src, dst, tid, nthr);
 }
 
 // Compile-time plan P = R0 R1 R2 (radix order as in Fft2Plan: the first pass runs the LAST radix; R2 = 1:

@@ -24,6 +24,11 @@ __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2_kernel(const __grid_
     extern __shared__ __align__(32) char nw_smem[];
     passA2_body<T, SP>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
+template <typename T, int CFG>
+__global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2p_kernel(const __grid_constant__ Long2Params<T> P) {
+    extern __shared__ __align__(32) char nw_smem[];
+    passA2p_body<T>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+}
 template <typename T, int MODE, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passB2_kernel(const __grid_constant__ Long2Params<T> P) {
     extern __shared__ __align__(32) char nw_smem[];
@@ -59,6 +64,7 @@ template <typename T, int CFG, int SP> static cudaError_t runB(const Long2Params
 #define NW_RUN_B(id) case id: return runB<NW_REAL, NW_CFG, id>(P, grid, nthr, smem, s);
 
 template <> cudaError_t prepare_long2<NW_REAL, NW_CFG>() {
+    { cudaError_t e = cudaFuncSetAttribute(nwcwt_passA2p_kernel<NW_REAL, NW_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
     NW_PREP_A(0) NW_SP_A(NW_PREP_A)
     NW_PREP_B(0) NW_SP_B(NW_PREP_B)
     return cudaSuccess;
@@ -70,6 +76,10 @@ template <> bool has_static_plan<NW_REAL, NW_CFG>(int pass, int sp) {
 }
 template <>
 cudaError_t launch_passA2<NW_REAL, NW_CFG>(int sp, const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
+    if (sp < 0) {   // pruned column transforms (per-frequency plans)
+        nwcwt_passA2p_kernel<NW_REAL, NW_CFG><<<grid, nthr, smem, s>>>(P);
+        return cudaGetLastError();
+    }
     switch (sp) {
         NW_SP_A(NW_RUN_A)
         default: return runA<NW_REAL, NW_CFG, 0>(P, grid, nthr, smem, s);

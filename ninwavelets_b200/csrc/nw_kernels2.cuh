@@ -34,6 +34,7 @@ struct Long2Params {
     cx<T>* Tm;          // intermediate ring, [rows][tm_stride]
     long long tm_stride;
     void* out;          // output of row 0 of the group
+    const PrunePlan* pplans;   // pruned pass A: plans indexed by FreqRec::pad_
     int row0;           // first row (signal-major: row = signal * F + frequency) of this launch
     int out_mode;
     SpecParams<T> sp;
@@ -76,24 +77,29 @@ template <typename T> struct TmDst2 {
     const Long2Params<T>* P;
     cx<T>* tm;
     int c;
+    int n1a;          // pruned transform: sequence t = tp * n1a + a computes rows n1 = a + n1a * b; else 1
+    fastdiv dn1a;
     struct Ctx {
         cx2<T> cur, g;
         cx<T>* col;
         uint32_t n1, step;
         bool valid, two;
     };
-    NW_HD Ctx begin(int base, int step, int tp) const {
+    NW_HD Ctx begin(int base, int step, int t) const {
         Ctx x;
         const int N2 = P->N2;
+        int tp = t, a = 0;
+        if (n1a > 1) { tp = (int)fd_div((uint32_t)t, dn1a); a = t - tp * n1a; }
         const int k2 = c + 2 * tp;
         x.valid = k2 < N2;
         x.two = k2 + 1 < N2;
         const int k2a = x.valid ? k2 : 0, k2b = x.two ? k2 + 1 : k2a;
-        x.cur = mk2<T>(big_twiddle2<T>(*P, k2a * base), big_twiddle2<T>(*P, k2b * base));
-        x.g = mk2<T>(big_twiddle2<T>(*P, k2a * step), big_twiddle2<T>(*P, k2b * step));
+        const int n1 = a + n1a * base, dn1 = n1a * step;
+        x.cur = mk2<T>(big_twiddle2<T>(*P, k2a * n1), big_twiddle2<T>(*P, k2b * n1));
+        x.g = mk2<T>(big_twiddle2<T>(*P, k2a * dn1), big_twiddle2<T>(*P, k2b * dn1));
         x.col = tm + ((size_t)k2a << (P->tpshB + 1));
-        x.n1 = (uint32_t)base;
-        x.step = (uint32_t)step;
+        x.n1 = (uint32_t)n1;
+        x.step = (uint32_t)dn1;
         return x;
     }
     template <int R> NW_HD void store_all(const Ctx& x, const cx2<T>* v) const {
@@ -150,10 +156,67 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(a, b);
     }
     NW_SYNC();
-    TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c};
+    TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c, 1, fastdiv{1, 0}};
     typedef StaticPlan<SP> S;
     if (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
     else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twA, buf, dst, tid, nthr);
+}
+
+// Pruned pass A.  A band that touches C <= n1b rows k1 gives every column a window of <= n1b consecutive k1;
+// with n1 = a + n1a b (n1a = N1 / n1b):   A[a + n1a b] = sum_j U_a[j] w_n1b^{j b},   U_a[k1 mod n1b] = Y[k1] w_N1^{k1 a}
+// - n1a transforms of length n1b per column instead of one of length N1 (log2 n1b levels instead of log2 N1).
+// The tile interleaves (column pair, phase a) sequences, a fastest, so natural-order results of neighbouring
+// lanes are consecutive rows n1 of the same column.
+template <typename T>
+NW_HD void passA2p_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
+    cx2<T>* buf = (cx2<T>*)smem;
+    const int tpsh = P.tpshA, TP = 1 << tpsh;
+    const int c = bx << (tpsh + 1);
+    const int gr = P.row0 + by;
+    const int si = gr / P.F, fi = gr - si * P.F;
+    const int N1 = P.N1, N2 = P.N2;
+    const FreqRec rec = P.sp.rec[fi];
+    const PrunePlan& pp = P.pplans[rec.pad_];
+    const int n1a = pp.n1a, n1b = pp.st.P, nseq = pp.nseq;
+    const cx<T>* X = P.X + (size_t)si * (size_t)P.N;
+    const int clast = (c + 2 * TP < N2 ? c + 2 * TP : N2) - 1;
+    int k1lo = rec.lo > clast ? (rec.lo - clast + N2 - 1) / N2 : 0;
+    int k1hi = rec.hi - 1 >= c ? (rec.hi - 1 - c) / N2 : -1;
+    if (k1hi > N1 - 1) k1hi = N1 - 1;
+    const int nk1 = k1hi - k1lo + 1;   // <= n1b by construction of the plan
+    const cx2<T> z = zero2<T>();
+    for (int i = tid; i < (N1 << tpsh); i += nthr) buf[i] = z;
+    NW_SYNC();
+    // one thread per in-band (row k1, column pair): evaluate Y once, write its n1a phase-shifted copies
+    // U_a = Y w_N1^{k1 a}; the table index k1 a mod N1 is kept incrementally
+    for (int i = tid; i < (nk1 << tpsh); i += nthr) {
+        const int tp = i & (TP - 1);
+        const int k1 = k1lo + (i >> tpsh);
+        const int k2 = c + 2 * tp;
+        const int k = k1 * N2 + k2;
+        cx<T> a = mk<T>((T)0, (T)0), b = a;
+        if (k2 < N2 && k >= rec.lo && k < rec.hi) a = spec_times<T>(P.sp, rec, fi, k, X[k]);
+        if (k2 + 1 < N2 && k + 1 >= rec.lo && k + 1 < rec.hi) b = spec_times<T>(P.sp, rec, fi, k + 1, X[k + 1]);
+        const cx2<T> y = mk2<T>(a, b);
+        const int j = k1 - (int)fd_div((uint32_t)k1, pp.dn1b) * n1b;
+        cx2<T>* slot = buf + (size_t)fft2_dit_pos(pp.st, j) * nseq + tp * n1a;
+        slot[0] = y;
+        int idx = 0;
+#pragma unroll 2
+        for (int q = 1; q < n1a; ++q) {
+            idx += k1;
+            if (idx >= N1) idx -= N1;
+            slot[q] = cmul_s(y, P.twA[idx]);
+        }
+    }
+    NW_SYNC();
+    TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c, n1a, pp.dn1a};
+    SeqDesc sq;
+    sq.tpsh = -1;
+    sq.nseq = nseq;
+    sq.twscale = n1a;
+    sq.d = pp.dseq;
+    fft2_dit<T, +1>(pp.st, sq, P.twA, buf, FromBuf(), dst, tid, nthr);
 }
 
 // ---- pass B --------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #pragma once
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -52,6 +53,8 @@ struct HostPlan {
     Fft2Plan stA2{}, stB2{};
     int nthrA2 = 256, nthrB2 = 256;
     int cfgA = 0, cfgB = 0;      // compiled launch shape (CFG2_*) of each pass
+    int pruneA = 0;              // pass A runs the pruned kernel (per-frequency PrunePlan, FreqRec::pad_)
+    std::vector<PrunePlan> pplans;
     size_t smem_A2 = 0, smem_B2 = 0;
     long long tm_stride2 = 0;
     int ring2 = 1;               // rows per pass-A / pass-B launch pair
@@ -353,6 +356,46 @@ inline void pick_threads2(const Fft2Plan& st, int tpsh, size_t smem, int ncfg, i
     }
 }
 
+inline int env_int(const char* name, int dflt);
+
+// Pruned pass A: per frequency the shortest packed-plannable divisor n1b of N1 that holds the rows k1 the band
+// touches.  Enabled when it shortens the column transform for at least half of the frequencies.
+inline void plan_prune(HostPlan& hp) {
+    hp.pruneA = 0;
+    hp.pplans.clear();
+    if (!hp.fast || hp.F <= 0 || env_int("NWCWT_NO_PRUNE", 0)) return;
+    const int N1 = hp.N1f, N2 = hp.N2f, TP = 1 << hp.tpshA;
+    std::vector<int> cand;
+    for (int d = 2; d <= N1; ++d) {
+        Fft2Plan t;
+        if (N1 % d == 0 && plan_packed(d, t)) cand.push_back(d);
+    }
+    std::vector<int> idx_of(N1 + 1, -1);
+    int shorter = 0;
+    for (int i = 0; i < hp.F; ++i) {
+        FreqRec& r = hp.rec[i];
+        const int C = r.hi > r.lo ? (r.hi - 1) / N2 - r.lo / N2 + 1 : 1;
+        int n1b = N1;
+        for (int d : cand) if (d >= C) { n1b = d; break; }
+        if (n1b < N1) ++shorter;
+        if (idx_of[n1b] < 0) {
+            PrunePlan pp;
+            memset(&pp, 0, sizeof(pp));
+            plan_packed(n1b, pp.st);
+            pp.n1a = N1 / n1b;
+            pp.nseq = TP * pp.n1a;
+            pp.dseq = make_fastdiv((uint32_t)pp.nseq);
+            pp.dn1a = make_fastdiv((uint32_t)pp.n1a);
+            pp.dn1b = make_fastdiv((uint32_t)n1b);
+            pp.dn1a1 = make_fastdiv((uint32_t)std::max(1, pp.n1a - 1));
+            idx_of[n1b] = (int)hp.pplans.size();
+            hp.pplans.push_back(pp);
+        }
+        r.pad_ = idx_of[n1b];
+    }
+    hp.pruneA = 2 * shorter >= hp.F;
+}
+
 inline int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e && *e ? atoi(e) : dflt;
@@ -489,6 +532,7 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
     long long ring = (long long)((48u << 20) / slot);
     hp.ring = (int)std::max<long long>(1, std::min<long long>(ring, 64));
     plan_shape_fast(hp);
+    plan_prune(hp);
     return true;
 }
 

@@ -90,6 +90,7 @@ struct nwcwt_plan {
     // device tables
     void *d_tw = nullptr, *d_twA = nullptr, *d_twB = nullptr, *d_twH = nullptr, *d_twL = nullptr;
     void *d_twA2 = nullptr, *d_twB2 = nullptr;   // fast long path
+    void* d_pplans = nullptr;                    // pruned pass A: PrunePlan[]
     // fast long path: launch pairs of consecutive row groups alternate between auxiliary streams so
     // that one group's pass A fills the SMs the previous group's pass-B tail leaves idle
     static const int MAX_AUX = 4;
@@ -213,6 +214,10 @@ static int ensure_device_t(nwcwt_plan* pl) {
         if (hp.fast) {
             if ((rc = upload_tw<T>(&pl->d_twA2, hp.N1f, hp.N1f, 1))) return rc;
             if ((rc = upload_tw<T>(&pl->d_twB2, hp.N2f, hp.N2f, 1))) return rc;
+            if (!hp.pplans.empty()) {
+                CUDA_TRY(cudaMalloc(&pl->d_pplans, sizeof(PrunePlan) * hp.pplans.size()));
+                CUDA_TRY(cudaMemcpy(pl->d_pplans, hp.pplans.data(), sizeof(PrunePlan) * hp.pplans.size(), cudaMemcpyHostToDevice));
+            }
         }
     }
     if (hp.F > 0) {
@@ -375,6 +380,7 @@ static Long2Params<T> make_long2(nwcwt_plan* pl) {
     P.twL = (const cx<T>*)pl->d_twL;
     P.lb = hp.lb;
     P.tm_stride = hp.tm_stride2;
+    P.pplans = (const PrunePlan*)pl->d_pplans;
     P.sp = make_spec<T>(pl);
     return P;
 }
@@ -417,6 +423,7 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
             // kernels specialised for this plan at compile time, where the library has them
             int spA = g_no_static ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = g_no_static ? 0 : static_plan_id(hp.stB2, hp.tpshB);
             if (!Long2Dispatch<T>::has(hp.cfgA, 0, spA)) spA = 0;
+            if (hp.pruneA && pl->d_pplans) spA = -1;
             if (!Long2Dispatch<T>::has(hp.cfgB, 1, spB)) spB = 0;
             if (ns > 1) {
                 CUDA_TRY(cudaEventRecord(pl->ev_fork, stream));
@@ -579,7 +586,7 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
     if (!pl) return 0;
     if (pl->on_device || pl->h_stream[0]) {
         cudaSetDevice(pl->hp.device);
-        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_twA2, pl->d_twB2,
+        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_twA2, pl->d_twB2, pl->d_pplans,
                         pl->h_in_dev[0], pl->h_in_dev[1], pl->h_out_dev[0], pl->h_out_dev[1], pl->h_ws[0], pl->h_ws[1]};
         for (void* p : ptrs)
             if (p) cudaFree(p);

@@ -148,13 +148,15 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
             char* smp = (char*)(((uintptr_t)sm2.data() + 31) & ~(uintptr_t)31);
             const int ntA = (g_mode & 4) ? 1 : hp.nthrA2, ntB = (g_mode & 4) ? 1 : hp.nthrB2;
             const long long rows = (long long)gs * hp.F;
-            const int spA = (g_mode & 8) ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = (g_mode & 8) ? 0 : static_plan_id(hp.stB2, hp.tpshB);
+            Q.pplans = hp.pplans.data();
+            const int spA = (hp.pruneA && !(g_mode & 16)) ? -1 : (g_mode & 8) ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = (g_mode & 8) ? 0 : static_plan_id(hp.stB2, hp.tpshB);
             for (long long r0 = 0; r0 < rows; r0 += ring2) {
                 const int g = (int)std::min<long long>(ring2, rows - r0);
                 Q.row0 = (int)r0;
                 for (int y = 0; y < g; ++y) for (int x = 0; x < tA; ++x)
                     Fibers::get().run(ntA, [&](int t) {
                         switch (spA) {
+                            case -1: passA2p_body<T>(Q, smp, x, y, t, ntA); break;
                             case 2: passA2_body<T, 2>(Q, smp, x, y, t, ntA); break;
                             case 4: passA2_body<T, 4>(Q, smp, x, y, t, ntA); break;
                             default: passA2_body<T, 0>(Q, smp, x, y, t, ntA); break;

@@ -64,6 +64,29 @@ def test_emul_long_path_forced(golden_transforms, name, dtype):
         assert l2_rel_err(z.astype(np.complex128), ref).max() <= F32_TOL
 
 
+@pytest.mark.parametrize("flags", [1, 1 | 16, 1 | 8 | 16, 1 | 2, 1 | 4])
+def test_emul_long_path_variants_agree(flags):
+    """Same input through every variant of the long path: pruned pass A (default), unpruned compile-time or
+    run-time plans (16, 8|16), generic kernels (2), one stepping thread instead of fibers (4)."""
+    rng = np.random.default_rng(11)
+    for kind, kw, n, freqs in (("morse", {}, 6000, np.array([1., 2.5, 9., 30., 77., 210., 499.])),
+                                ("morlet", dict(sigma=7.0), 3600, np.arange(1., 60., 7.)),
+                                ("mexicanhat", {}, 3000, np.array([2., 8., 40.])),
+                                ("shannon", {}, 2400, np.array([1., 2.])),
+                                ("morse", dict(interpolate=True), 4500, np.array([3., 50., 400.]))):
+        fam = orc.Family(kind, sfreq=1000.0, **kw)
+        x = rng.standard_normal((2, n))
+        ref = np.stack([orc.cwt(fam, xi, freqs) for xi in x])
+        d = desc_from_oracle_family(fam, freqs, n, dtype=1)
+        z = emul_transform(d, x, output=0, force_long=flags)
+        assert peak_rel_err(z.reshape(-1, n), ref.reshape(-1, n)).max() <= F64_TOL, (kind, flags)
+        d32 = desc_from_oracle_family(fam, freqs, n, dtype=0)
+        x32 = x.astype(np.float32)
+        ref32 = np.stack([orc.power(fam, xi.astype(np.float64), freqs) for xi in x32])
+        p = emul_transform(d32, x32, output=2, force_long=flags)
+        assert l2_rel_err(p.reshape(-1, n), ref32.reshape(-1, n)).max() <= F32_TOL, (kind, flags)
+
+
 def test_emul_long_65536(golden_transforms):
     c = golden_transforms["morse_long_n65536"]
     fam = orc.Family(c["kind"], **c["kw"])
