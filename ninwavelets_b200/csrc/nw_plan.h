@@ -363,7 +363,10 @@ inline int env_int(const char* name, int dflt);
 inline void plan_prune(HostPlan& hp) {
     hp.pruneA = 0;
     hp.pplans.clear();
-    if (!hp.fast || hp.F <= 0 || env_int("NWCWT_NO_PRUNE", 0)) return;
+    // r01 measurement (profiles/r01/shape_sweep.md): with run-time plans the pruned kernel executes as many
+    // instructions as the unpruned compile-time-plan kernel and stalls on its phase-table loads (22.6 vs
+    // 15.4 ms per cfg2 step), so it is opt-in (NWCWT_PRUNE=1) until it has compile-time plans of its own.
+    if (!hp.fast || hp.F <= 0 || !env_int("NWCWT_PRUNE", 0)) return;
     const int N1 = hp.N1f, N2 = hp.N2f, TP = 1 << hp.tpshA;
     std::vector<int> cand;
     for (int d = 2; d <= N1; ++d) {

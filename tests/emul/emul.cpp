@@ -210,6 +210,7 @@ extern "C" int emul_transform(const nwcwt_plan_desc* d, const void* signals, voi
     plan_bands(hp);
     std::string err;
     g_mode = force_long;
+    setenv("NWCWT_PRUNE", (force_long & 16) ? "0" : "1", 1);   // the emulation exercises the pruned pass A by default
     if (!plan_shape(hp, err, (force_long & 1) != 0)) {
         strncpy(errbuf, err.c_str(), errlen - 1);
         return -2;
