@@ -94,7 +94,8 @@ typedef struct nwcwt_plan_info {
     int64_t n;
     int32_t n_freqs;
     int32_t path;          /* 0 = short rows (one CTA per signal), 1 = long rows (two passes, generic
-                              kernels), 2 = long rows (two passes, packed in-place kernels) */
+                              kernels), 2 = long rows (two passes, packed in-place kernels), 3 = short rows
+                              (packed in-place kernel, one CTA per signal pair) */
     int32_t n1, n2;        /* long rows: n = n1 * n2 */
     int32_t batch;         /* frequencies (short) / columns (long) interleaved per CTA */
     int32_t n_stages[2];   /* radix stages of the n (short) or n1, n2 (long) point transforms */

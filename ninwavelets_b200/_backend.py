@@ -172,7 +172,7 @@ class Plan:
     def info(self):
         i = PlanInfo()
         _check(lib().nwcwt_plan_get_info(self._h, C.byref(i)))
-        out = dict(n=i.n, n_freqs=i.n_freqs, path=("short", "long", "long_packed")[i.path], n1=i.n1, n2=i.n2,
+        out = dict(n=i.n, n_freqs=i.n_freqs, path=("short", "long", "long_packed", "short_packed")[i.path], n1=i.n1, n2=i.n2,
                    batch=i.batch, band_bins=i.band_bins, smem_bytes=i.smem_bytes, threads=list(i.threads),
                    rows_per_launch=i.rows_per_launch)
         out["radices"] = [list(i.radices[k][: i.n_stages[k]]) for k in range(2)]

@@ -180,7 +180,7 @@ template <typename T, int DIR, bool RAW0, int TPS, int P, int R0, int R1, int R2
 NW_HD void fft2_dif_static(const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid, int nthr) {
     dif_body<T, R0, DIR, false, RAW0>(GeoStat<P, 1, R0, TPS, RevNone>(), tw, buf, dst, tid, nthr);
     NW_SYNC();
-    if (R2 > 1) {
+    if constexpr (R2 > 1) {
         dif_body<T, R1, DIR, false, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, dst, tid, nthr);
         NW_SYNC();
         dif_body<T, (R2 > 1 ? R2 : 2), DIR, true, false>(GeoStat<P, R0 * R1, (R2 > 1 ? R2 : 2), TPS, Rev3<R0, R1>>(), tw, buf, dst, tid, nthr);
@@ -304,7 +304,7 @@ NW_HD void fft2_dit(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, c
 template <typename T, int DIR, int TPS, int P, int R0, int R1, int R2, class Dst>
 NW_HD void fft2_dit_static(const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid, int nthr) {
     const FromBuf src;
-    if (R2 > 1) {
+    if constexpr (R2 > 1) {
         dit_body<T, (R2 > 1 ? R2 : 2), DIR, true, false>(GeoStat<P, R0 * R1, (R2 > 1 ? R2 : 2), TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
         NW_SYNC();
         dit_body<T, R1, DIR, false, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);

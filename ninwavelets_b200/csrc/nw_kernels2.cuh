@@ -47,7 +47,9 @@ template <> struct StaticPlan<2> { static const int P = 600, R0 = 12, R1 = 10, R
 template <> struct StaticPlan<3> { static const int P = 1024, R0 = 16, R1 = 16, R2 = 4, TPS = 2; };
 template <> struct StaticPlan<4> { static const int P = 256, R0 = 16, R1 = 16, R2 = 1, TPS = 2; };
 template <> struct StaticPlan<5> { static const int P = 512, R0 = 16, R1 = 8, R2 = 4, TPS = 2; };
-static const int N_STATIC_PLANS = 5;
+template <> struct StaticPlan<6> { static const int P = 1500, R0 = 10, R1 = 10, R2 = 15, TPS = 1; };   // short rows, cfg3
+template <> struct StaticPlan<7> { static const int P = 300, R0 = 12, R1 = 5, R2 = 5, TPS = 3; };      // short rows, cfg1
+static const int N_STATIC_PLANS = 7;
 template <int ID> NW_HD bool static_plan_matches(const Fft2Plan& st, int tpsh) {
     typedef StaticPlan<ID> S;
     if (st.P != S::P || tpsh != S::TPS) return false;
@@ -61,6 +63,8 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     if (static_plan_matches<3>(st, tpsh)) return 3;
     if (static_plan_matches<4>(st, tpsh)) return 4;
     if (static_plan_matches<5>(st, tpsh)) return 5;
+    if (static_plan_matches<6>(st, tpsh)) return 6;
+    if (static_plan_matches<7>(st, tpsh)) return 7;
     return 0;
 }
 
@@ -158,7 +162,7 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     NW_SYNC();
     TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c, 1, fastdiv{1, 0}};
     typedef StaticPlan<SP> S;
-    if (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
+    if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
     else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twA, buf, dst, tid, nthr);
 }
 
@@ -301,7 +305,7 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
     LongOutDst2<T, MODE> dst{(char*)P.out + (size_t)gr * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
     typedef StaticPlan<SP> S;
-    if (SP == 0) fft2_dif<T, +1, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
+    if constexpr (SP == 0) fft2_dif<T, +1, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
     else fft2_dif_static<T, +1, true, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
 }
 

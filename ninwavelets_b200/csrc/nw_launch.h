@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "nw_kernels.cuh"
 #include "nw_kernels2.cuh"
+#include "nw_kernels3.cuh"
 
 namespace nw {
 template <typename T> cudaError_t prepare_short();
@@ -24,4 +25,9 @@ template <typename T, int CFG>
 cudaError_t launch_passA2(int sp, const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
 template <typename T, int CFG>
 cudaError_t launch_passB2(int sp, const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+// fused short-row kernel on the packed engine (nw_kernels3.cuh); sp = StaticPlan id of the inverse transform
+template <typename T> cudaError_t prepare_short2();
+template <typename T> bool has_static_short2(int sp);
+template <typename T>
+cudaError_t launch_short2(int sp, const Short2Params<T>& P, unsigned grid, int nthr, size_t smem, cudaStream_t s);
 }  // namespace nw

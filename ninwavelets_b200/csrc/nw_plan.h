@@ -47,6 +47,10 @@ struct HostPlan {
     int nthr_short = 256, nthr_long = 512;
     long long tm_stride = 0;
     int ring = 1;                // rows (and signals) in flight on the long path
+    // fused short-row kernel on the packed engine (nw_kernels3.cuh); 0 = not available (generic kernel is used)
+    int short2 = 0, tpshS = 0, nthrS2 = 256;
+    Fft2Plan stS{};
+    size_t smem_S2 = 0;
     // fast long path (packed in-place engine, nw_kernels2.cuh); 0 = not available for this N
     int fast = 0;
     int N1f = 0, N2f = 0, tpshA = 0, tpshB = 0;
@@ -463,6 +467,33 @@ inline void plan_shape_fast(HostPlan& hp) {
     hp.ring2 = (int)std::max<long long>(1, std::min<long long>(ring, 256));
 }
 
+// Packed-engine short kernel: N 2-3-5 smooth, N (1 + NF) two-lane complex values of shared memory with NF = 1, 2, 4
+// or 8 frequencies per pass - as many as keep three CTAs per SM (75 KB), at least one.
+inline void plan_shape_short2(HostPlan& hp) {
+    hp.short2 = 0;
+    if (hp.N < 8 || hp.N > 16384 || env_int("NWCWT_NO_SHORT2", 0)) return;
+    Fft2Plan st;
+    if (!plan_packed(hp.N, st)) return;
+    const size_t c2 = 2 * cx_size(hp.dtype);
+    int fcap = 0;
+    while ((1 << fcap) < hp.F && fcap < 3) ++fcap;
+    const int forced = env_int("NWCWT_TPSH_S", -1);
+    int pick = -1;
+    for (int t = fcap; t >= 0 && pick < 0; --t)
+        if ((size_t)hp.N * (1 + ((size_t)1 << t)) * c2 + 512 <= 75 * 1024) pick = t;
+    if (pick < 0 && (size_t)hp.N * 2 * c2 + 512 <= SMEM_MAX) pick = 0;
+    if (forced >= 0 && (size_t)hp.N * (1 + ((size_t)1 << forced)) * c2 + 512 <= SMEM_MAX) pick = forced;
+    if (pick < 0) return;
+    hp.short2 = 1;
+    hp.tpshS = pick;
+    hp.stS = st;
+    hp.smem_S2 = (size_t)hp.N * (1 + ((size_t)1 << pick)) * c2 + 512;
+    long long maxnb = 0;
+    for (int s = 0; s < st.nst; ++s) maxnb = std::max(maxnb, (long long)(st.P / st.radix[s]) << pick);
+    hp.nthrS2 = (int)std::min<long long>(256, std::max<long long>(64, (maxnb + 31) / 32 * 32));
+    hp.nthrS2 = env_int("NWCWT_NTHR_S", hp.nthrS2);
+}
+
 inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) {
     const size_t cs = cx_size(hp.dtype);
     const long long N = hp.N;
@@ -487,6 +518,7 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
                     long long work = N * tt / 8;
                     int nt = (int)std::min<long long>(512, std::max<long long>(64, (work + 31) / 32 * 32));
                     hp.nthr_short = nt;
+                    plan_shape_short2(hp);
                     return true;
                 }
             }

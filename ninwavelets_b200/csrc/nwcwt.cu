@@ -237,6 +237,7 @@ static int ensure_device_t(nwcwt_plan* pl) {
     // opt in to large dynamic shared memory
     if (hp.path == 0) {
         CUDA_TRY(prepare_short<T>());
+        if (hp.short2) CUDA_TRY(prepare_short2<T>());
     } else {
         CUDA_TRY(prepare_passA<T>());
         CUDA_TRY(prepare_passB<T>());
@@ -293,10 +294,47 @@ static int device_sms(int device) {
     return n;
 }
 
+// fused short-row kernel on the packed engine: one CTA per signal pair (and frequency share)
+template <typename T>
+static int launch_short2(nwcwt_plan* pl, const void* signals, void* out, long long S, int output, int bl, long long blo,
+                         long long bhi, cudaStream_t stream) {
+    const HostPlan& hp = pl->hp;
+    Short2Params<T> P;
+    memset(&P, 0, sizeof(P));
+    P.signals = (const T*)signals;
+    P.out = out;
+    P.N = (int)hp.N;
+    P.F = hp.F;
+    P.S = (int)S;
+    P.tpsh = hp.tpshS;
+    P.out_mode = output;
+    P.bl_mode = bl;
+    P.bl_lo = (int)blo;
+    P.bl_hi = (int)bhi;
+    P.st = hp.stS;
+    P.tw = (const cx<T>*)pl->d_tw;
+    P.sp = make_spec<T>(pl);
+    const long long npairs = (S + 1) / 2;
+    const int ngroups = (hp.F + (1 << hp.tpshS) - 1) >> hp.tpshS;
+    const long long target = 6LL * device_sms(hp.device);
+    long long fs = (target + npairs - 1) / npairs;
+    if (fs > ngroups) fs = ngroups;
+    if (fs < 1) fs = 1;
+    P.fsplit = (int)fs;
+    const long long grid = npairs * fs;
+    if (grid > 2147483647LL) return fail(NWCWT_ERR_INVALID, "too many signals for one launch");
+    int sp = g_no_static ? 0 : static_plan_id(hp.stS, hp.tpshS);
+    if (!has_static_short2<T>(sp)) sp = 0;
+    { LaunchScope ls(0, stream); CUDA_TRY(launch_short2<T>(sp, P, (unsigned)grid, hp.nthrS2, hp.smem_S2, stream)); }
+    return 0;
+}
+
 template <typename T>
 static int launch_short(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
                         int bl, long long blo, long long bhi, cudaStream_t stream, bool forward_only) {
     const HostPlan& hp = pl->hp;
+    if (hp.short2 && !forward_only && !g_force_generic)
+        return launch_short2<T>(pl, signals, out, S, output, bl, blo, bhi, stream);
     ShortParams<T> P;
     memset(&P, 0, sizeof(P));
     P.signals = (const T*)signals;
@@ -616,6 +654,14 @@ int nwcwt_plan_get_info(const nwcwt_plan* pl, nwcwt_plan_info* info) {
         for (int i = 0; i < hp.st.nst; ++i) info->radices[0][i] = hp.st.radix[i];
         info->smem_bytes = (int64_t)hp.smem_short;
         info->threads[0] = hp.nthr_short;
+        if (hp.short2) {
+            info->path = 3;
+            info->batch = 1 << hp.tpshS;
+            info->n_stages[0] = hp.stS.nst;
+            for (int i = 0; i < hp.stS.nst; ++i) info->radices[0][i] = hp.stS.radix[i];
+            info->smem_bytes = (int64_t)hp.smem_S2;
+            info->threads[0] = hp.nthrS2;
+        }
     } else if (hp.fast) {
         info->n1 = hp.N1f;
         info->n2 = hp.N2f;

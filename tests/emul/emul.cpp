@@ -15,6 +15,7 @@
 #include "../../ninwavelets_b200/csrc/nw_family.cuh"
 #include "../../ninwavelets_b200/csrc/nw_kernels.cuh"
 #include "../../ninwavelets_b200/csrc/nw_kernels2.cuh"
+#include "../../ninwavelets_b200/csrc/nw_kernels3.cuh"
 #include "../../ninwavelets_b200/csrc/nw_plan.h"
 
 #include <ucontext.h>
@@ -93,6 +94,28 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
     sp.norm = (T)(1.0 / (double)hp.N);
     sp.rec = hp.rec.data(); sp.table = table.data(); sp.table_len = hp.table_len;
     const size_t esz = output == OUT_CWT ? sizeof(cx<T>) : sizeof(T);
+    if (hp.path == 0 && hp.short2 && !(g_mode & 2)) {
+        std::vector<cx<T>> tw;
+        fill_tw<T>(tw, hp.N, hp.N, 1);
+        Short2Params<T> P;
+        memset(&P, 0, sizeof(P));
+        P.signals = (const T*)signals; P.out = out; P.N = (int)hp.N; P.F = hp.F; P.S = (int)S; P.tpsh = hp.tpshS;
+        P.out_mode = output; P.bl_mode = bl; P.bl_lo = (int)blo; P.bl_hi = (int)bhi; P.st = hp.stS; P.tw = tw.data(); P.sp = sp;
+        const int ngroups = (hp.F + (1 << hp.tpshS) - 1) >> hp.tpshS;
+        P.fsplit = ngroups < 3 ? ngroups : 3;
+        std::vector<char> sm(hp.smem_S2 + 64);
+        char* smp = (char*)(((uintptr_t)sm.data() + 31) & ~(uintptr_t)31);
+        const int nt = (g_mode & 4) ? 1 : hp.nthrS2;
+        const int spS = (g_mode & 8) ? 0 : static_plan_id(hp.stS, hp.tpshS);
+        const long long nblk = ((S + 1) / 2) * P.fsplit;
+        for (long long b = 0; b < nblk; ++b)
+            Fibers::get().run(nt, [&](int t) {
+                if (output == OUT_POWER) { if (spS == 6) short2_body<T, OUT_POWER, 6>(P, smp, (int)b, t, nt); else if (spS == 7) short2_body<T, OUT_POWER, 7>(P, smp, (int)b, t, nt); else short2_body<T, OUT_POWER, 0>(P, smp, (int)b, t, nt); }
+                else if (output == OUT_ABS) short2_body<T, OUT_ABS, 0>(P, smp, (int)b, t, nt);
+                else { if (spS == 6) short2_body<T, OUT_CWT, 6>(P, smp, (int)b, t, nt); else short2_body<T, OUT_CWT, 0>(P, smp, (int)b, t, nt); }
+            });
+        return 0;
+    }
     if (hp.path == 0) {
         std::vector<cx<T>> tw;
         fill_tw<T>(tw, hp.N, hp.N, 1);

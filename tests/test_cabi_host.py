@@ -30,9 +30,11 @@ def plan(n, freqs, family=be.MORSE, dtype=np.float32, **kw):
 
 def test_short_and_long_shapes():
     i = plan(300, np.arange(1, 100.0)).info()
-    assert i["path"] == "short" and i["batch"] == 8 and np.prod(i["radices"][0]) == 300
+    assert i["path"] == "short_packed" and i["batch"] == 8 and np.prod(i["radices"][0]) == 300
     i = plan(1500, np.arange(1, 101.0)).info()
-    assert i["path"] == "short" and np.prod(i["radices"][0]) == 1500 and i["smem_bytes"] <= 227 * 1024
+    assert i["path"] == "short_packed" and np.prod(i["radices"][0]) == 1500 and i["smem_bytes"] <= 75 * 1024
+    i = plan(2 * 7 * 11 * 13, np.arange(1, 101.0)).info()   # a factor the packed engine does not have: generic kernel
+    assert i["path"] == "short" and np.prod(i["radices"][0]) == 2002
     i = plan(600000, np.arange(1, 101.0)).info()
     assert i["path"] == "long_packed" and i["n1"] * i["n2"] == 600000
     assert np.prod(i["radices"][0]) == i["n1"] and np.prod(i["radices"][1]) == i["n2"]
