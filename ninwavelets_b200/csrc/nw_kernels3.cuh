@@ -33,7 +33,7 @@ struct Short2Params {
 };
 
 template <typename T> NW_HD size_t short2_smem_bytes(int N, int tpsh) {
-    return (size_t)N * (1 + ((size_t)1 << tpsh)) * sizeof(cx2<T>) + 64 * sizeof(double);
+    return (size_t)N * (1 + ((size_t)1 << tpsh)) * sizeof(cx2<T>) + 160 * sizeof(double);
 }
 
 // forward: two real signals as the two lanes
@@ -99,13 +99,14 @@ NW_HD void short2_body(const Short2Params<T>& P, char* smem, int bx, int tid, in
     typedef StaticPlan<SP> SPL;
     const int ngroups = (P.F + NF - 1) >> tpsh;
     const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
+    // the tile starts as zeros; every pass re-zeroes the slots it reads on the way out
+    const cx2<T> z = zero2<T>();
+    for (int i = tid; i < (N << tpsh); i += nthr) buf[i] = z;
+    NW_SYNC();
     for (int g = part; g < ngroups; g += P.fsplit) {
         const int f0 = g << tpsh;
         const int nvalid = (P.F - f0 < NF) ? (P.F - f0) : NF;
-        // ---- tile = 0, then the in-band products -------------------------------------------------
-        const cx2<T> z = zero2<T>();
-        for (int i = tid; i < (N << tpsh); i += nthr) buf[i] = z;
-        NW_SYNC();
+        // ---- the in-band products into the zero tile ------------------------------------------------
         for (int t = 0; t < nvalid; ++t) {
             const int fi = f0 + t;
             const FreqRec rec = P.sp.rec[fi];
@@ -135,37 +136,63 @@ NW_HD void short2_body(const Short2Params<T>& P, char* smem, int bx, int tid, in
         const bool blon = MODE != OUT_CWT && P.bl_mode != BL_NONE;
         const bool uselog = P.bl_mode == BL_LOG || P.bl_mode == BL_ZLOG;
         if (blon) {
+            // window statistics of every row (np.mean / np.std, ddof = 0; base.py:49-50, 65): sums of d = x - x[lo]
+            // and d^2 in fp64, the window of a row split over the warps the CTA has per row
+            const int cnt = P.bl_hi - P.bl_lo;
 #if defined(__CUDA_ARCH__)
             const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-            for (int r = warp; r < nrows; r += nwarp) {
+            const int wpr = nwarp / nrows > 0 ? (nwarp / nrows > 4 ? 4 : nwarp / nrows) : 1;   // warps per row
+            for (int job = warp; job < nrows * wpr; job += nwarp) {
+                const int r = job / wpr, part = job - r * wpr;
                 const int t = r >> 1, l = r & 1;
-                double s = 0.0;
-                for (int i = P.bl_lo + lane; i < P.bl_hi; i += 32) {
-                    const pk<T> p = buf[((size_t)i << tpsh) + t].re;
-                    s += (double)(l ? pk_hi(p) : pk_lo(p));
+                double s = 0.0, q = 0.0;
+                if (cnt > 0) {
+                    const pk<T> p0 = buf[((size_t)P.bl_lo << tpsh) + t].re;
+                    const double x0 = (double)(l ? pk_hi(p0) : pk_lo(p0));
+                    for (int i = P.bl_lo + part * 32 + lane; i < P.bl_hi; i += 32 * wpr) {
+                        const pk<T> p = buf[((size_t)i << tpsh) + t].re;
+                        const double d = (double)(l ? pk_hi(p) : pk_lo(p)) - x0;
+                        s += d;
+                        q += d * d;
+                    }
                 }
-                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                const int cnt = P.bl_hi - P.bl_lo;
-                const double m = cnt > 0 ? s / cnt : nan("");
-                double q = 0.0;
-                for (int i = P.bl_lo + lane; i < P.bl_hi; i += 32) {
-                    const pk<T> p = buf[((size_t)i << tpsh) + t].re;
-                    const double d = (double)(l ? pk_hi(p) : pk_lo(p)) - m;
-                    q += d * d;
+                for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+                if (lane == 0) { rstat[32 + 2 * (r * 4 + part)] = s; rstat[32 + 2 * (r * 4 + part) + 1] = q; }
+            }
+            NW_SYNC();
+            if (tid < nrows) {
+                const int r = tid, t = r >> 1, l = r & 1;
+                double s = 0.0, q = 0.0;
+                for (int part = 0; part < wpr; ++part) { s += rstat[32 + 2 * (r * 4 + part)]; q += rstat[32 + 2 * (r * 4 + part) + 1]; }
+                double m = nan(""), sd = nan("");
+                if (cnt > 0) {
+                    const pk<T> p0 = buf[((size_t)P.bl_lo << tpsh) + t].re;
+                    const double x0 = (double)(l ? pk_hi(p0) : pk_lo(p0));
+                    const double ms = s / cnt;
+                    double var = q / cnt - ms * ms;
+                    if (var < 0.0) var = 0.0;
+                    m = x0 + ms;
+                    sd = sqrt(var);
                 }
-                for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-                if (lane == 0) { rstat[2 * r] = m; rstat[2 * r + 1] = cnt > 0 ? sqrt(q / cnt) : nan(""); }
+                rstat[2 * r] = m;
+                rstat[2 * r + 1] = sd;
             }
 #else
             for (int r = tid; r < nrows; r += nthr) {
                 const int t = r >> 1, l = r & 1;
-                const int cnt = P.bl_hi - P.bl_lo;
-                double s = 0.0, q = 0.0;
-                for (int i = P.bl_lo; i < P.bl_hi; ++i) { const pk<T> p = buf[((size_t)i << tpsh) + t].re; s += (double)(l ? pk_hi(p) : pk_lo(p)); }
-                const double m = cnt > 0 ? s / cnt : nan("");
-                for (int i = P.bl_lo; i < P.bl_hi; ++i) { const pk<T> p = buf[((size_t)i << tpsh) + t].re; const double d = (double)(l ? pk_hi(p) : pk_lo(p)) - m; q += d * d; }
-                rstat[2 * r] = m;
-                rstat[2 * r + 1] = cnt > 0 ? sqrt(q / cnt) : nan("");
+                double s = 0.0, q = 0.0, x0 = 0.0;
+                if (cnt > 0) { const pk<T> p0 = buf[((size_t)P.bl_lo << tpsh) + t].re; x0 = (double)(l ? pk_hi(p0) : pk_lo(p0)); }
+                for (int i = P.bl_lo; i < P.bl_hi; ++i) {
+                    const pk<T> p = buf[((size_t)i << tpsh) + t].re;
+                    const double d = (double)(l ? pk_hi(p) : pk_lo(p)) - x0;
+                    s += d;
+                    q += d * d;
+                }
+                const double ms = cnt > 0 ? s / cnt : 0.0;
+                double var = cnt > 0 ? q / cnt - ms * ms : 0.0;
+                if (var < 0.0) var = 0.0;
+                rstat[2 * r] = cnt > 0 ? x0 + ms : nan("");
+                rstat[2 * r + 1] = cnt > 0 ? sqrt(var) : nan("");
             }
 #endif
             NW_SYNC();
@@ -191,6 +218,7 @@ NW_HD void short2_body(const Short2Params<T>& P, char* smem, int bx, int tid, in
             char* row1 = row0 + (size_t)P.F * (size_t)N * esz;
             for (int n = tid; n < N; n += nthr) {
                 const cx2<T> v = buf[((size_t)n << tpsh) + t];
+                buf[((size_t)n << tpsh) + t] = z;   // the next pass gathers into a zero tile
                 if (MODE == OUT_CWT) {
                     ((cx<T>*)row0)[n] = lane0(v);
                     if (has1) ((cx<T>*)row1)[n] = lane1(v);

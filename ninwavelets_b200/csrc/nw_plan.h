@@ -480,14 +480,14 @@ inline void plan_shape_short2(HostPlan& hp) {
     const int forced = env_int("NWCWT_TPSH_S", -1);
     int pick = -1;
     for (int t = fcap; t >= 0 && pick < 0; --t)
-        if ((size_t)hp.N * (1 + ((size_t)1 << t)) * c2 + 512 <= 75 * 1024) pick = t;
-    if (pick < 0 && (size_t)hp.N * 2 * c2 + 512 <= SMEM_MAX) pick = 0;
-    if (forced >= 0 && (size_t)hp.N * (1 + ((size_t)1 << forced)) * c2 + 512 <= SMEM_MAX) pick = forced;
+        if ((size_t)hp.N * (1 + ((size_t)1 << t)) * c2 + 1280 <= 75 * 1024) pick = t;
+    if (pick < 0 && (size_t)hp.N * 2 * c2 + 1280 <= SMEM_MAX) pick = 0;
+    if (forced >= 0 && (size_t)hp.N * (1 + ((size_t)1 << forced)) * c2 + 1280 <= SMEM_MAX) pick = forced;
     if (pick < 0) return;
     hp.short2 = 1;
     hp.tpshS = pick;
     hp.stS = st;
-    hp.smem_S2 = (size_t)hp.N * (1 + ((size_t)1 << pick)) * c2 + 512;
+    hp.smem_S2 = (size_t)hp.N * (1 + ((size_t)1 << pick)) * c2 + 1280;
     long long maxnb = 0;
     for (int s = 0; s < st.nst; ++s) maxnb = std::max(maxnb, (long long)(st.P / st.radix[s]) << pick);
     hp.nthrS2 = (int)std::min<long long>(256, std::max<long long>(64, (maxnb + 31) / 32 * 32));
