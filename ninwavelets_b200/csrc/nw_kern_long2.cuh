@@ -29,6 +29,16 @@ __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2p_kernel(const __grid
     extern __shared__ __align__(32) char nw_smem[];
     passA2p_body<T>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
+template <typename T, int CFG>
+__global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2f_kernel(const __grid_constant__ Long2Params<T> P) {
+    extern __shared__ __align__(32) char nw_smem[];
+    passA2f_body<T>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+}
+template <typename T, int CFG>
+__global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passB2f_kernel(const __grid_constant__ Long2Params<T> P) {
+    extern __shared__ __align__(32) char nw_smem[];
+    passB2_body<T, OUT_CWT, 0, -1>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+}
 template <typename T, int MODE, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passB2_kernel(const __grid_constant__ Long2Params<T> P) {
     extern __shared__ __align__(32) char nw_smem[];
@@ -64,6 +74,8 @@ template <typename T, int CFG, int SP> static cudaError_t runB(const Long2Params
 #define NW_RUN_B(id) case id: return runB<NW_REAL, NW_CFG, id>(P, grid, nthr, smem, s);
 
 template <> cudaError_t prepare_long2<NW_REAL, NW_CFG>() {
+    { cudaError_t e = cudaFuncSetAttribute(nwcwt_passA2f_kernel<NW_REAL, NW_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
+    { cudaError_t e = cudaFuncSetAttribute(nwcwt_passB2f_kernel<NW_REAL, NW_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
     { cudaError_t e = cudaFuncSetAttribute(nwcwt_passA2p_kernel<NW_REAL, NW_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
     NW_PREP_A(0) NW_SP_A(NW_PREP_A)
     NW_PREP_B(0) NW_SP_B(NW_PREP_B)
@@ -76,6 +88,10 @@ template <> bool has_static_plan<NW_REAL, NW_CFG>(int pass, int sp) {
 }
 template <>
 cudaError_t launch_passA2<NW_REAL, NW_CFG>(int sp, const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
+    if (sp == -2) {   // forward transform
+        nwcwt_passA2f_kernel<NW_REAL, NW_CFG><<<grid, nthr, smem, s>>>(P);
+        return cudaGetLastError();
+    }
     if (sp < 0) {   // pruned column transforms (per-frequency plans)
         nwcwt_passA2p_kernel<NW_REAL, NW_CFG><<<grid, nthr, smem, s>>>(P);
         return cudaGetLastError();
@@ -87,6 +103,10 @@ cudaError_t launch_passA2<NW_REAL, NW_CFG>(int sp, const Long2Params<NW_REAL>& P
 }
 template <>
 cudaError_t launch_passB2<NW_REAL, NW_CFG>(int sp, const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
+    if (sp == -2) {   // forward transform
+        nwcwt_passB2f_kernel<NW_REAL, NW_CFG><<<grid, nthr, smem, s>>>(P);
+        return cudaGetLastError();
+    }
     switch (sp) {
         NW_SP_B(NW_RUN_B)
         default: return runB<NW_REAL, NW_CFG, 0>(P, grid, nthr, smem, s);

@@ -30,6 +30,7 @@ struct Long2Params {
     const cx<T>* twH;   // w_N^{j << lb}
     const cx<T>* twL;   // w_N^{j}, j < 1 << lb
     int lb;
+    const T* signal;    // forward transform: real signals of this launch, [nsig][N]
     const cx<T>* X;     // spectra of the signals of this group, [nsig][N]
     cx<T>* Tm;          // intermediate ring, [rows][tm_stride]
     long long tm_stride;
@@ -68,16 +69,17 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     return 0;
 }
 
-template <typename T> NW_HD cx<T> big_twiddle2(const Long2Params<T>& P, int m) {
+template <typename T, int DIR = 1> NW_HD cx<T> big_twiddle2(const Long2Params<T>& P, int m) {
     const cx<T> a = P.twH[m >> P.lb];
     const cx<T> b = P.twL[m & ((1 << P.lb) - 1)];
-    return cmul(a, b);
+    const cx<T> w = cmul(a, b);
+    return DIR > 0 ? w : mk<T>(w.x, -w.y);
 }
 
 // ---- pass A --------------------------------------------------------------------------------
 // natural-order results n1 = base + q * step of columns k2, k2 + 1, times w_N^{k2 n1}: the factor runs
 // as a geometric sequence in q (ratio w_N^{k2 step}), two table look-ups per lane and butterfly
-template <typename T> struct TmDst2 {
+template <typename T, int DIR = 1> struct TmDst2 {
     const Long2Params<T>* P;
     cx<T>* tm;
     int c;
@@ -99,8 +101,8 @@ template <typename T> struct TmDst2 {
         x.two = k2 + 1 < N2;
         const int k2a = x.valid ? k2 : 0, k2b = x.two ? k2 + 1 : k2a;
         const int n1 = a + n1a * base, dn1 = n1a * step;
-        x.cur = mk2<T>(big_twiddle2<T>(*P, k2a * n1), big_twiddle2<T>(*P, k2b * n1));
-        x.g = mk2<T>(big_twiddle2<T>(*P, k2a * dn1), big_twiddle2<T>(*P, k2b * dn1));
+        x.cur = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * n1), big_twiddle2<T, DIR>(*P, k2b * n1));
+        x.g = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * dn1), big_twiddle2<T, DIR>(*P, k2b * dn1));
         x.col = tm + ((size_t)k2a << (P->tpshB + 1));
         x.n1 = (uint32_t)n1;
         x.step = (uint32_t)dn1;
@@ -164,6 +166,28 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     typedef StaticPlan<SP> S;
     if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
     else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twA, buf, dst, tid, nthr);
+}
+
+// Forward transform, pass A (scipy.fftpack.fft of the signal, base.py:399): the same column pass with the
+// conjugate kernel; input = the real signal itself (every bin), row index = signal.
+template <typename T>
+NW_HD void passA2f_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
+    cx2<T>* buf = (cx2<T>*)smem;
+    const int tpsh = P.tpshA, TP = 1 << tpsh;
+    const int c = bx << (tpsh + 1);
+    const int N1 = P.N1, N2 = P.N2;
+    const T* x = P.signal + (size_t)(P.row0 + by) * (size_t)P.N;
+    for (int i = tid; i < (N1 << tpsh); i += nthr) {
+        const int tp = i & (TP - 1);
+        const int k1 = i >> tpsh;
+        const int k2 = c + 2 * tp;
+        const size_t k = (size_t)k1 * N2 + k2;
+        const T a = k2 < N2 ? x[k] : (T)0, b = k2 + 1 < N2 ? x[k + 1] : (T)0;
+        buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(pk_make(a, b), pk_bcast((T)0));
+    }
+    NW_SYNC();
+    TmDst2<T, -1> dst{&P, P.Tm + (size_t)by * P.tm_stride, c, 1, fastdiv{1, 0}};
+    fft2_dit<T, -1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
 }
 
 // Pruned pass A.  A band that touches C <= n1b rows k1 gives every column a window of <= n1b consecutive k1;
@@ -276,7 +300,8 @@ template <typename T, int MODE> struct LongOutDst2 {
     }
 };
 
-template <typename T, int MODE, int SP>
+// DIR = -1: forward transform, pass B: P.out is the spectrum buffer [nsig][N] (MODE = OUT_CWT)
+template <typename T, int MODE, int SP, int DIR = 1>
 NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
     const int shB = P.tpshB + 1;
     const int TB = 1 << shB;
@@ -305,8 +330,8 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
     LongOutDst2<T, MODE> dst{(char*)P.out + (size_t)gr * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
     typedef StaticPlan<SP> S;
-    if constexpr (SP == 0) fft2_dif<T, +1, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
-    else fft2_dif_static<T, +1, true, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
+    if constexpr (SP == 0) fft2_dif<T, DIR, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
+    else fft2_dif_static<T, DIR, true, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
 }
 
 }  // namespace nw

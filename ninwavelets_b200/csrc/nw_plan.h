@@ -57,6 +57,7 @@ struct HostPlan {
     Fft2Plan stA2{}, stB2{};
     int nthrA2 = 256, nthrB2 = 256;
     int cfgA = 0, cfgB = 0;      // compiled launch shape (CFG2_*) of each pass
+    int generic_ok = 1;          // long path: the generic two-pass kernels also have a plan for this N
     int pruneA = 0;              // pass A runs the pruned kernel (per-frequency PrunePlan, FreqRec::pad_)
     std::vector<PrunePlan> pplans;
     size_t smem_A2 = 0, smem_B2 = 0;
@@ -550,8 +551,17 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
             if (score > bestScore) { bestScore = score; best1 = n1; bestTA = ta; bestTB = tb; }
         }
     }
-    if (!best1) { err = "no usable two-pass split for this length (prime factor > 64 or length > 2^30)"; return false; }
     hp.path = 1;
+    hp.lb = (ilog2_floor(N) + 2) / 2;
+    plan_shape_fast(hp);
+    if (!best1) {
+        if (!hp.fast) { err = "no usable two-pass split for this length (prime factor > 64 or length > 2^30)"; return false; }
+        // only the packed kernels can take this length (tiles too large for the generic engine's two buffers)
+        hp.generic_ok = 0;
+        hp.ring = (int)std::max<long long>(1, std::min<long long>(64, (256LL << 20) / (N * (long long)cs)));
+        plan_prune(hp);
+        return true;
+    }
     hp.N1 = (int)best1;
     hp.N2 = (int)(N / best1);
     if (!factorise(hp.N1, hp.stA, err) || !factorise(hp.N2, hp.stB, err)) return false;
@@ -560,13 +570,11 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
     hp.tshB = ilog2_floor(bestTB);
     hp.smem_A = 2 * (size_t)hp.N1 * hp.pitchA * cs;
     hp.smem_B = 2 * (size_t)hp.N2 * bestTB * cs + 16;
-    hp.lb = (ilog2_floor(N) + 2) / 2;
     const long long nblk = (hp.N1 + bestTB - 1) / bestTB;
     hp.tm_stride = nblk * hp.N2 * bestTB;
     const size_t slot = (size_t)hp.tm_stride * cs;
     long long ring = (long long)((48u << 20) / slot);
     hp.ring = (int)std::max<long long>(1, std::min<long long>(ring, 64));
-    plan_shape_fast(hp);
     plan_prune(hp);
     return true;
 }

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) nwcwt_reduce_kernel(const void* in, T* ou
 // ---------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static bool g_no_static = getenv("NWCWT_NO_STATIC") != nullptr;   // tuning: run-time plans only
+static bool g_fwd_generic = getenv("NWCWT_FWD_GENERIC") != nullptr;   // tuning: forward transform on the generic kernels
 static bool g_force_generic = false;   // nwcwt_debug_force_generic: run the generic kernels even where a fast path exists
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -206,8 +207,10 @@ static int ensure_device_t(nwcwt_plan* pl) {
     if (hp.path == 0) {
         if ((rc = upload_tw<T>(&pl->d_tw, hp.N, hp.N, 1))) return rc;
     } else {
-        if ((rc = upload_tw<T>(&pl->d_twA, hp.N1, hp.N1, 1))) return rc;
-        if ((rc = upload_tw<T>(&pl->d_twB, hp.N2, hp.N2, 1))) return rc;
+        if (hp.generic_ok) {
+            if ((rc = upload_tw<T>(&pl->d_twA, hp.N1, hp.N1, 1))) return rc;
+            if ((rc = upload_tw<T>(&pl->d_twB, hp.N2, hp.N2, 1))) return rc;
+        }
         const long long nL = 1LL << hp.lb, nH = (hp.N + nL - 1) / nL;
         if ((rc = upload_tw<T>(&pl->d_twL, nL, hp.N, 1))) return rc;
         if ((rc = upload_tw<T>(&pl->d_twH, nH, hp.N, nL))) return rc;
@@ -437,15 +440,34 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
     LongParams<T> P = make_long<T>(pl);
     P.Tm = Tm;
     const int TA = 1 << hp.tshA, TB = 1 << hp.tshB;
-    const unsigned tilesA = (unsigned)((hp.N2 + TA - 1) / TA), tilesB = (unsigned)((hp.N1 + TB - 1) / TB);
+    const unsigned tilesA = hp.generic_ok ? (unsigned)((hp.N2 + TA - 1) / TA) : 0u, tilesB = hp.generic_ok ? (unsigned)((hp.N1 + TB - 1) / TB) : 0u;
     const size_t esz = (output == NWCWT_OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
     for (long long s0 = 0; s0 < S; s0 += hp.ring) {
         const int gs = (int)std::min<long long>(hp.ring, S - s0);
         // forward transforms of gs signals (scipy.fftpack.fft, base.py:399)
-        P.signal = (const T*)signals + (size_t)s0 * hp.N;
-        P.Xout = forward_only ? (cx<T>*)spectra_out + (size_t)s0 * hp.N : X;
-        { LaunchScope ls(1, stream); CUDA_TRY(launch_passA<T>(-1, P, dim3(tilesA, gs), hp.nthr_long, hp.smem_A, stream)); }
-        { LaunchScope ls(2, stream); CUDA_TRY(launch_passB<T>(-1, P, dim3(tilesB, gs), hp.nthr_long, hp.smem_B, stream)); }
+        cx<T>* Xdst = forward_only ? (cx<T>*)spectra_out + (size_t)s0 * hp.N : X;
+        if (hp.fast && !g_force_generic && !g_fwd_generic) {
+            // packed kernels, conjugate transform; chunks of ring2 signals share the first Tm slot
+            Long2Params<T> Qf = make_long2<T>(pl);
+            Qf.Tm = Tm;
+            Qf.out_mode = NWCWT_OUT_CWT;
+            const unsigned tA = (unsigned)((hp.N2f + (2 << hp.tpshA) - 1) / (2 << hp.tpshA));
+            const unsigned tB = (unsigned)((hp.N1f + (2 << hp.tpshB) - 1) / (2 << hp.tpshB));
+            for (int c0 = 0; c0 < gs; c0 += hp.ring2) {
+                const int gc = std::min(hp.ring2, gs - c0);
+                Qf.signal = (const T*)signals + (size_t)(s0 + c0) * hp.N;
+                Qf.out = Xdst + (size_t)c0 * hp.N;
+                Qf.row0 = 0;
+                { LaunchScope ls(1, stream); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, -2, Qf, dim3(tA, gc), hp.nthrA2, hp.smem_A2, stream)); }
+                { LaunchScope ls(2, stream); CUDA_TRY(Long2Dispatch<T>::B(hp.cfgB, -2, Qf, dim3(tB, gc), hp.nthrB2, hp.smem_B2, stream)); }
+            }
+        } else {
+            if (!hp.generic_ok) return fail(NWCWT_ERR_UNSUPPORTED, "this length has no generic two-pass plan (packed kernels only)");
+            P.signal = (const T*)signals + (size_t)s0 * hp.N;
+            P.Xout = Xdst;
+            { LaunchScope ls(1, stream); CUDA_TRY(launch_passA<T>(-1, P, dim3(tilesA, gs), hp.nthr_long, hp.smem_A, stream)); }
+            { LaunchScope ls(2, stream); CUDA_TRY(launch_passB<T>(-1, P, dim3(tilesB, gs), hp.nthr_long, hp.smem_B, stream)); }
+        }
         if (forward_only) continue;
         if (hp.fast && !g_force_generic) {
             // inverse transforms of all gs * F rows of the group, ring2 rows per launch pair
@@ -488,6 +510,7 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
             }
             continue;
         }
+        if (!hp.generic_ok) return fail(NWCWT_ERR_UNSUPPORTED, "this length has no generic two-pass plan (packed kernels only)");
         for (int si = 0; si < gs; ++si) {
             P.X = X + (size_t)si * hp.N;
             char* out_s = (char*)out + (size_t)(s0 + si) * hp.F * (size_t)hp.N * esz;

@@ -131,8 +131,10 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
         return 0;
     }
     std::vector<cx<T>> twA, twB, twH, twL;
-    fill_tw<T>(twA, hp.N1, hp.N1, 1);
-    fill_tw<T>(twB, hp.N2, hp.N2, 1);
+    if (hp.generic_ok) {
+        fill_tw<T>(twA, hp.N1, hp.N1, 1);
+        fill_tw<T>(twB, hp.N2, hp.N2, 1);
+    }
     const long long nL = 1LL << hp.lb, nH = (hp.N + nL - 1) / nL;
     fill_tw<T>(twL, nL, hp.N, 1);
     fill_tw<T>(twH, nH, hp.N, nL);
@@ -145,14 +147,38 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
     std::vector<cx<T>> X((size_t)ring * hp.N), Tm((size_t)ring * hp.tm_stride);
     P.Tm = Tm.data();
     const int TA = 1 << hp.tshA, TB = 1 << hp.tshB;
-    const int tilesA = (hp.N2 + TA - 1) / TA, tilesB = (hp.N1 + TB - 1) / TB;
+    const int tilesA = hp.generic_ok ? (hp.N2 + TA - 1) / TA : 0, tilesB = hp.generic_ok ? (hp.N1 + TB - 1) / TB : 0;
     std::vector<char> smem(std::max(hp.smem_A, hp.smem_B) + 64);
     for (long long s0 = 0; s0 < S; s0 += ring) {
         const int gs = (int)std::min<long long>(ring, S - s0);
+        if (hp.fast && !(g_mode & 2) && !(g_mode & 32)) {
+            std::vector<cx<T>> twA2, twB2;
+            fill_tw<T>(twA2, hp.N1f, hp.N1f, 1);
+            fill_tw<T>(twB2, hp.N2f, hp.N2f, 1);
+            Long2Params<T> Q;
+            memset(&Q, 0, sizeof(Q));
+            Q.N = hp.N; Q.N1 = hp.N1f; Q.N2 = hp.N2f; Q.F = hp.F; Q.tpshA = hp.tpshA; Q.tpshB = hp.tpshB;
+            Q.stA = hp.stA2; Q.stB = hp.stB2; Q.twA = twA2.data(); Q.twB = twB2.data(); Q.twH = twH.data(); Q.twL = twL.data();
+            Q.lb = hp.lb; Q.tm_stride = hp.tm_stride2; Q.out_mode = OUT_CWT;
+            std::vector<cx<T>> Tmf((size_t)hp.tm_stride2);
+            Q.Tm = Tmf.data();
+            const int tA = (hp.N2f + (2 << hp.tpshA) - 1) / (2 << hp.tpshA), tB = (hp.N1f + (2 << hp.tpshB) - 1) / (2 << hp.tpshB);
+            std::vector<char> sm2(std::max(hp.smem_A2, hp.smem_B2) + 64);
+            char* smp = (char*)(((uintptr_t)sm2.data() + 31) & ~(uintptr_t)31);
+            const int ntA = (g_mode & 4) ? 1 : hp.nthrA2, ntB = (g_mode & 4) ? 1 : hp.nthrB2;
+            for (int y = 0; y < gs; ++y) {
+                Q.signal = (const T*)signals + (size_t)(s0 + y) * hp.N;
+                Q.out = X.data() + (size_t)y * hp.N;
+                Q.row0 = 0;
+                for (int x = 0; x < tA; ++x) Fibers::get().run(ntA, [&](int t) { passA2f_body<T>(Q, smp, x, 0, t, ntA); });
+                for (int x = 0; x < tB; ++x) Fibers::get().run(ntB, [&](int t) { passB2_body<T, OUT_CWT, 0, -1>(Q, smp, x, 0, t, ntB); });
+            }
+        } else {
         P.signal = (const T*)signals + (size_t)s0 * hp.N;
         P.Xout = X.data();
         for (int y = 0; y < gs; ++y) for (int x = 0; x < tilesA; ++x) passA_body<T, -1>(P, smem.data(), x, y, 0, 1);
         for (int y = 0; y < gs; ++y) for (int x = 0; x < tilesB; ++x) passB_body<T, -1>(P, smem.data(), x, y, 0, 1);
+        }
         if (hp.fast && !(g_mode & 2)) {
             std::vector<cx<T>> twA2, twB2;
             fill_tw<T>(twA2, hp.N1f, hp.N1f, 1);

@@ -235,3 +235,66 @@ def test_forward_fft_entry_point(nw):
         X = plan.forward_device(torch.as_tensor(x, device="cuda")).cpu().numpy()
         ref = np.fft.fft(x, axis=1)
         assert np.abs(X - ref).max() / np.abs(ref).max() <= 1e-14, n
+
+
+@pytest.mark.parametrize("kind,kw", [("morse", dict(sfreq=1000)), ("morlet", dict(sfreq=1000, sigma=7.)),
+                                     ("morlet", dict(sfreq=1000, sigma=7., gabor=True)), ("shannon", dict(sfreq=1000)),
+                                     ("mexicanhat", dict(sfreq=1000))])
+def test_family_sweep_at_2_20(nw, kind, kw):
+    """BASELINE.json config 4: every family at N = 2^20 against the oracle (fp32 tolerance, fp64 on one family)."""
+    n = 1 << 20
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(n)
+    fr = np.array([1.0, 9.0, 60.0, 128.0])
+    fam = orc.Family(kind, **kw)
+    x32 = x.astype(np.float32)
+    ref = orc.power(fam, x32.astype(np.float64), fr)
+    p = make(nw, kind, kw, dtype="float32").power(x32, fr)
+    assert l2_rel_err(p.astype(np.float64), ref).max() <= F32_TOL, kind
+    if kind == "morse":
+        z = make(nw, kind, kw, dtype="float64").cwt(x, fr)
+        assert peak_rel_err(z, orc.cwt(fam, x, fr)).max() <= F64_TOL
+
+
+@pytest.mark.parametrize("e", [16, 18, 22, 24])
+def test_long_signal_sweep_vs_oracle(nw, e):
+    """BASELINE.json config 5 sizes that the oracle can still hold: two frequencies, fp32 and (up to 2^22) fp64."""
+    n = 1 << e
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(n)
+    fr = np.array([3.0, 200.0])
+    fam = orc.Family("morse", sfreq=1000)
+    x32 = x.astype(np.float32)
+    ref = orc.power(fam, x32.astype(np.float64), fr)
+    p = make(nw, "morse", dict(sfreq=1000), dtype="float32").power(x32, fr)
+    assert l2_rel_err(p.astype(np.float64), ref).max() <= F32_TOL, e
+    del p, ref
+    if e <= 24:
+        z = make(nw, "morse", dict(sfreq=1000), dtype="float64").cwt(x, fr)
+        assert peak_rel_err(z, orc.cwt(fam, x, fr)).max() <= F64_TOL, e
+
+
+def test_2_26_properties(nw):
+    """N = 2^26 (config 5's largest row; only the packed kernels have a plan): Parseval and linearity in fp32."""
+    import torch
+    n = 1 << 26
+    rng = np.random.default_rng(6)
+    a = rng.standard_normal(n).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    fr = np.array([5.0, 120.0])
+    m = make(nw, "morse", dict(sfreq=1000), dtype="float32")
+    ta, tb = torch.as_tensor(a, device="cuda")[None], torch.as_tensor(b, device="cuda")[None]
+    za = m.cwt(ta, fr)[0]
+    zb = m.cwt(tb, None)[0]
+    zab = m.cwt(ta + 2 * tb, None)[0]
+    d = (zab - (za + 2 * zb))
+    num = torch.sqrt((d.real.double() ** 2 + d.imag.double() ** 2).sum(dim=1))
+    den = torch.sqrt((zab.real.double() ** 2 + zab.imag.double() ** 2).sum(dim=1))
+    assert float((num / den).max()) <= 20 * F32_TOL
+    X = torch.fft.fft(ta[0].double())
+    k = np.arange(n) * (1 / (n / 1000.0))
+    for i, f in enumerate(fr):
+        W = torch.as_tensor(orc.analytic_spectrum(orc.Family("morse"), k, f), device="cuda")
+        lhs = float((za[i].real.double() ** 2 + za[i].imag.double() ** 2).sum())
+        rhs = float(((W * X).abs() ** 2).sum()) / n
+        assert abs(lhs - rhs) / rhs <= 100 * F32_TOL
