@@ -5,8 +5,8 @@
 //                generation x signal spectrum (base.py:236-248, 404) gathered straight into a
 //                decimation-in-time N1-point transform; natural-order results times w_N^{k2 n1}
 //                go to the L2-resident intermediate Tm in TB-blocked layout.
-//   passB2_body  rows: one bulk (TMA) copy brings a tile of TB = 2*TPB consecutive n1 x all k2 into
-//                shared memory, a decimation-in-frequency N2-point transform runs in place, and
+//   passB2_body  rows: one bulk (TMA) copy brings a tile of TB = 2*TPB consecutive n1 x all k2 (already in the
+//                engine's lane-packed units) into shared memory, a decimation-in-frequency N2-point transform runs in place, and
 //                the |z|^2 / |z| / z epilogue (base.py:425, 443) stores straight from registers -
 //                each n2 gives TB consecutive output samples (32-byte sectors for fp32, TB = 8).
 // Both bodies compile for the host as well (tests/emul steps them block by block).
@@ -113,15 +113,24 @@ template <typename T, int DIR = 1> struct TmDst2 {
         const int shB = P->tpshB + 1;
         const uint32_t mask = (1u << shB) - 1u;
         const uint32_t blk = (uint32_t)P->N2 << shB;        // elements per block of 2^shB rows
-        cx2<T> cur = x.cur;
+        // two interleaved recurrences (even / odd q, ratio g^2) halve the dependency chain
+        cx2<T> cur[2] = {x.cur, cmul_p(x.cur, x.g)};
+        const cx2<T> g2 = cmul_p(x.g, x.g);
         uint32_t n1 = x.n1;
 #pragma unroll
         for (int q = 0; q < R; ++q, n1 += x.step) {
-            const cx2<T> y = cmul_p(v[q], cur);
-            if (q + 1 < R) cur = cmul_p(cur, x.g);
-            cx<T>* o = x.col + (size_t)((n1 >> shB) * blk + (n1 & mask));
-            o[0] = lane0(y);
-            if (x.two) o[(size_t)1 << shB] = lane1(y);
+            const cx2<T> y = cmul_p(v[q], cur[q & 1]);
+            if (q + 2 < R) cur[q & 1] = cmul_p(cur[q & 1], g2);
+            // Tm holds lane-packed units {re(n1), re(n1+1), im(n1), im(n1+1)} per (k2, row pair): pass B's tile needs no
+            // repacking, and the four scalars go out straight from the packed registers
+            const size_t e = (size_t)((n1 >> shB) * blk + (n1 & mask));          // complex index within the column pair's rows
+            T* o = (T*)x.col + (((e >> 1) << 2) + (n1 & 1u));
+            o[0] = pk_lo(y.re);
+            o[2] = pk_lo(y.im);
+            if (x.two) {
+                o[(size_t)2 << shB] = pk_hi(y.re);
+                o[((size_t)2 << shB) + 2] = pk_hi(y.im);
+            }
         }
     }
 };
@@ -330,8 +339,8 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
     LongOutDst2<T, MODE> dst{(char*)P.out + (size_t)gr * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
     typedef StaticPlan<SP> S;
-    if constexpr (SP == 0) fft2_dif<T, DIR, true>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
-    else fft2_dif_static<T, DIR, true, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
+    if constexpr (SP == 0) fft2_dif<T, DIR, false>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
+    else fft2_dif_static<T, DIR, false, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
 }
 
 }  // namespace nw

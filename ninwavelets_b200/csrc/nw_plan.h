@@ -423,6 +423,7 @@ inline void plan_shape_fast(HostPlan& hp) {
             const long long n1 = cand[w], n2 = N / n1;
             if (w == 1 && n1 == n2) continue;
             if (n1 > 32768 || n2 > 32768) continue;
+            if (env_int("NWCWT_SPLIT_N1", 0) > 0 && n1 != env_int("NWCWT_SPLIT_N1", 0)) continue;   // tuning override
             Fft2Plan a, b;
             if (!plan_packed(n1, a) || !plan_packed(n2, b)) continue;
             const int fa = env_int("NWCWT_TPSH_A", -1), fb = env_int("NWCWT_TPSH_B", -1);   // tuning overrides
