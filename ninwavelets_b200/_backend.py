@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnwcwt.so")
+LIB_PATH = os.environ.get("NWCWT_LIB") or os.path.join(_HERE, "libnwcwt.so")   # NWCWT_LIB: experiment builds
 
 F32, F64 = 0, 1
 MORSE, MORLET, SHANNON, TABLE = 0, 1, 2, 3

@@ -55,6 +55,17 @@ template <int DIR, typename T> NW_HD cx<T> rot(cx<T> v) {
     return DIR > 0 ? mk<T>(-v.y, v.x) : mk<T>(v.y, -v.x);
 }
 
+// ---- streaming (evict-first) stores for results that are written once and never re-read by the kernels:
+// they must not push the L2-resident intermediate out of the cache
+#if defined(__CUDA_ARCH__)
+NW_D void st_stream(float* p, float v) { __stcs(p, v); }
+NW_D void st_stream(double* p, double v) { __stcs(p, v); }
+NW_D void st_stream(cx<float>* p, cx<float> v) { __stcs((float2*)p, make_float2(v.x, v.y)); }
+NW_D void st_stream(cx<double>* p, cx<double> v) { __stcs((double2*)p, make_double2(v.x, v.y)); }
+#else
+template <typename U> inline void st_stream(U* p, U v) { *p = v; }
+#endif
+
 // ---- exact division by a small runtime constant ------------------------------
 // q = x / d for every x with x*d < 2^32 (checked by the planner): one
 // multiply-high.  m == 0 encodes d == 1.

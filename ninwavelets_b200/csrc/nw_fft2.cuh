@@ -117,15 +117,29 @@ NW_HD void dif_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
         if (LAST) ctx = dst.begin(g.rev(blk), g.P / R, tp);   // issues the epilogue's own loads early
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = RAW ? raw_to_packed<T>(e[r * stride]) : e[r * stride];
+#if !defined(NW_KNOCKOUT) || NW_KNOCKOUT != 1
         B2<T, R, DIR>::run(v);
+#endif
         if (LAST) {
             dst.template store_all<R>(ctx, v);
         } else {
+#if defined(NW_KNOCKOUT) && NW_KNOCKOUT == 1      /* timing experiment: no arithmetic */
+#pragma unroll
+            for (int r = 0; r < R; ++r) e[r * stride] = v[r];
+#elif defined(NW_KNOCKOUT) && NW_KNOCKOUT == 2    /* timing experiment: no shared-memory stores */
+            cx<T> w[R];
+            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * g.tws]), w);
+            cx2<T> acc = v[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) acc = acc + cmul_s(v[r], w[r]);
+            if (pk_lo(acc.re) == (T)123.456) e[0] = acc;
+#else
             cx<T> w[R];
             tw_powers<T, R>(tw_dir<T, DIR>(tw[np * g.tws]), w);
             e[0] = v[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) e[r * stride] = cmul_s(v[r], w[r]);
+#endif
         }
     }
 }

@@ -36,6 +36,9 @@ struct Long2Params {
     long long tm_stride;
     void* out;          // output of row 0 of the group
     const PrunePlan* pplans;   // pruned pass A: plans indexed by FreqRec::pad_
+    int skew, skew_mod; // start-up stagger of the first wave: CTA waits ((linear block id / n_sm) % skew_mod) * skew cycles
+    int n_sm;
+    int tm_mod;         // timing experiment only: rows share Tm slots (by % tm_mod); 0 = off
     int row0;           // first row (signal-major: row = signal * F + frequency) of this launch
     int out_mode;
     SpecParams<T> sp;
@@ -67,6 +70,24 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     if (static_plan_matches<6>(st, tpsh)) return 6;
     if (static_plan_matches<7>(st, tpsh)) return 7;
     return 0;
+}
+
+// CTAs of one launch start together and, doing identical work, would run their load / butterfly / store phases in
+// lockstep, leaving the FP32 pipe idle while all of them load and the LSU idle while all of them compute.  A one-time
+// stagger of the first wave (later CTAs inherit it from the slot they take over) de-phases the CTAs of an SM.
+template <typename T> NW_HD void first_wave_stagger(const Long2Params<T>& P, int bx, int by, int gx) {
+#if defined(__CUDA_ARCH__)
+    if (P.skew > 0) {
+        const unsigned lin = (unsigned)by * (unsigned)gx + (unsigned)bx;
+        if (lin < (unsigned)(P.n_sm * P.skew_mod)) {
+            const long long wait = (long long)((lin / (unsigned)P.n_sm) % (unsigned)P.skew_mod) * P.skew;
+            const long long t0 = clock64();
+            while (clock64() - t0 < wait) {}
+        }
+    }
+#else
+    (void)P; (void)bx; (void)by; (void)gx;
+#endif
 }
 
 template <typename T, int DIR = 1> NW_HD cx<T> big_twiddle2(const Long2Params<T>& P, int m) {
@@ -157,6 +178,7 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     int k1hi = rec.hi - 1 >= c ? (rec.hi - 1 - c) / N2 : -1;
     if (k1hi > N1 - 1) k1hi = N1 - 1;
     const int nk1 = k1hi - k1lo + 1;
+    first_wave_stagger<T>(P, bx, by, (N2 + 2 * TP - 1) / (2 * TP));
     const cx2<T> z = zero2<T>();
     for (int i = tid; i < (N1 << tpsh); i += nthr) buf[i] = z;
     NW_SYNC();
@@ -171,7 +193,7 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(a, b);
     }
     NW_SYNC();
-    TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c, 1, fastdiv{1, 0}};
+    TmDst2<T> dst{&P, P.Tm + (size_t)(P.tm_mod > 0 ? by % P.tm_mod : by) * P.tm_stride, c, 1, fastdiv{1, 0}};
     typedef StaticPlan<SP> S;
     if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
     else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twA, buf, dst, tid, nthr);
@@ -283,8 +305,8 @@ template <typename T, int MODE> struct LongOutDst2 {
             cx<T>* o = (cx<T>*)out + idx;
 #pragma unroll
             for (int q = 0; q < R; ++q, o += dstep) {
-                o[0] = lane0(v[q]);
-                if (two) o[1] = lane1(v[q]);
+                st_stream(o, lane0(v[q]));
+                if (two) st_stream(o + 1, lane1(v[q]));
             }
             return;
         }
@@ -294,16 +316,16 @@ template <typename T, int MODE> struct LongOutDst2 {
             for (int q = 0; q < R; ++q, o += dstep) {
                 if (MODE == OUT_POWER) {
                     const pk<T> p = pk_fma(v[q].im, v[q].im, v[q].re * v[q].re);
-                    *(cx<T>*)o = mk<T>(pk_lo(p), pk_hi(p));   // one 2*sizeof(T) store
+                    st_stream((cx<T>*)o, mk<T>(pk_lo(p), pk_hi(p)));   // one 2*sizeof(T) store
                 } else {
-                    *(cx<T>*)o = mk<T>(nw_hypot(pk_lo(v[q].re), pk_lo(v[q].im)), nw_hypot(pk_hi(v[q].re), pk_hi(v[q].im)));
+                    st_stream((cx<T>*)o, mk<T>(nw_hypot(pk_lo(v[q].re), pk_lo(v[q].im)), nw_hypot(pk_hi(v[q].re), pk_hi(v[q].im))));
                 }
             }
         } else {
 #pragma unroll
             for (int q = 0; q < R; ++q, o += dstep) {
-                o[0] = real_out<T>(MODE, lane0(v[q]));
-                if (two) o[1] = real_out<T>(MODE, lane1(v[q]));
+                st_stream(o, real_out<T>(MODE, lane0(v[q])));
+                if (two) st_stream(o + 1, real_out<T>(MODE, lane1(v[q])));
             }
         }
     }
@@ -316,7 +338,7 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const int TB = 1 << shB;
     cx2<T>* buf = (cx2<T>*)smem;
     const size_t tile_elems = (size_t)P.N2 << shB;   // complex values
-    const cx<T>* tile = P.Tm + (size_t)by * P.tm_stride + (size_t)bx * tile_elems;
+    const cx<T>* tile = P.Tm + (size_t)(P.tm_mod > 0 ? by % P.tm_mod : by) * P.tm_stride + (size_t)bx * tile_elems;
 #if defined(__CUDA_ARCH__)
     const size_t bytes = tile_elems * sizeof(cx<T>);
     uint64_t* bar = (uint64_t*)((char*)smem + bytes);
@@ -331,6 +353,7 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         }
     }
     mbar_wait(bar, 0);
+    first_wave_stagger<T>(P, bx, by, (P.N1 + TB - 1) / TB);
 #else
     for (size_t i = tid; i < tile_elems; i += nthr) ((cx<T>*)smem)[i] = tile[i];
     NW_SYNC();

@@ -220,8 +220,8 @@ NW_HD void short2_body(const Short2Params<T>& P, char* smem, int bx, int tid, in
                 const cx2<T> v = buf[((size_t)n << tpsh) + t];
                 buf[((size_t)n << tpsh) + t] = z;   // the next pass gathers into a zero tile
                 if (MODE == OUT_CWT) {
-                    ((cx<T>*)row0)[n] = lane0(v);
-                    if (has1) ((cx<T>*)row1)[n] = lane1(v);
+                    st_stream((cx<T>*)row0 + n, lane0(v));
+                    if (has1) st_stream((cx<T>*)row1 + n, lane1(v));
                 } else {
                     T y0 = pk_lo(v.re), y1 = pk_hi(v.re);
                     if (blon) {
@@ -229,8 +229,8 @@ NW_HD void short2_body(const Short2Params<T>& P, char* smem, int bx, int tid, in
                         y1 = (y1 + b1) * a1;
                         if (uselog) { y0 = nw_log10(y0) * c0; y1 = nw_log10(y1) * c1; }
                     }
-                    ((T*)row0)[n] = y0;
-                    if (has1) ((T*)row1)[n] = y1;
+                    st_stream((T*)row0 + n, y0);
+                    if (has1) st_stream((T*)row1 + n, y1);
                 }
             }
         }

@@ -73,6 +73,10 @@ __global__ void __launch_bounds__(256) nwcwt_reduce_kernel(const void* in, T* ou
 static thread_local std::string g_err;
 static bool g_no_static = getenv("NWCWT_NO_STATIC") != nullptr;   // tuning: run-time plans only
 static bool g_fwd_generic = getenv("NWCWT_FWD_GENERIC") != nullptr;   // tuning: forward transform on the generic kernels
+static int env_i(const char* n, int d) { const char* e = getenv(n); return e && *e ? atoi(e) : d; }
+static int g_skew_a = env_i("NWCWT_SKEW_A", 0), g_skew_mod_a = env_i("NWCWT_SKEW_MOD_A", 5);
+static int g_skew_b = env_i("NWCWT_SKEW_B", 0), g_skew_mod_b = env_i("NWCWT_SKEW_MOD_B", 3);
+static int g_tm_mod = env_i("NWCWT_TM_MOD", 0);   // timing experiment: wrong results
 static bool g_force_generic = false;   // nwcwt_debug_force_generic: run the generic kernels even where a fast path exists
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -98,6 +102,10 @@ struct nwcwt_plan {
     cudaStream_t aux[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {nullptr, nullptr, nullptr, nullptr};
     int n_aux = 0;
+    // L2 residency of the intermediate: persisting carve-out + access-policy window on the Tm ring
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    const void* l2_window_base = nullptr;
+    size_t l2_window_bytes = 0;
     void* d_rec = nullptr;
     void* d_table = nullptr;
     // host-call resources
@@ -247,6 +255,14 @@ static int ensure_device_t(nwcwt_plan* pl) {
         if (hp.fast) {
             CUDA_TRY(Long2Dispatch<T>::prepare(hp.cfgA));
             CUDA_TRY(Long2Dispatch<T>::prepare(hp.cfgB));
+            if (!getenv("NWCWT_NO_L2_PERSIST")) {
+                int v = 0;
+                cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, hp.device);
+                pl->l2_persist_max = (size_t)(v > 0 ? v : 0);
+                cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, hp.device);
+                pl->l2_window_max = (size_t)(v > 0 ? v : 0);
+                if (pl->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, pl->l2_persist_max);
+            }
             int ns = 2;
             if (const char* e = getenv("NWCWT_STREAMS")) ns = atoi(e);
             ns = ns < 1 ? 1 : ns > nwcwt_plan::MAX_AUX ? nwcwt_plan::MAX_AUX : ns;
@@ -489,6 +505,23 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
                 CUDA_TRY(cudaEventRecord(pl->ev_fork, stream));
                 for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(pl->aux[i], pl->ev_fork, 0));
             }
+            // keep the Tm slots in use resident in L2 (hit -> persisting, everything else on these streams streams)
+            {
+                const size_t used = (size_t)std::max(ns, 1) * (size_t)hp.ring2 * (size_t)hp.tm_stride2 * sizeof(cx<T>);
+                if (pl->l2_persist_max && pl->l2_window_max && (pl->l2_window_base != (const void*)Tm || pl->l2_window_bytes != used)) {
+                    cudaStreamAttrValue av;
+                    memset(&av, 0, sizeof(av));
+                    av.accessPolicyWindow.base_ptr = (void*)Tm;
+                    av.accessPolicyWindow.num_bytes = std::min(used, pl->l2_window_max);
+                    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)pl->l2_persist_max / (double)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    if (ns > 1) for (int i = 0; i < ns; ++i) cudaStreamSetAttribute(pl->aux[i], cudaStreamAttributeAccessPolicyWindow, &av);
+                    else cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+                    pl->l2_window_base = (const void*)Tm;
+                    pl->l2_window_bytes = used;
+                }
+            }
             int gi = 0;
             for (long long r0 = 0; r0 < rows; r0 += hp.ring2, ++gi) {
                 const int g = (int)std::min<long long>(hp.ring2, rows - r0);
@@ -496,7 +529,11 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
                 cudaStream_t st = ns > 1 ? pl->aux[slot] : stream;
                 Q.row0 = (int)r0;
                 Q.Tm = Tm + (size_t)slot * (size_t)hp.ring2 * (size_t)hp.tm_stride2;
+                Q.n_sm = device_sms(hp.device);
+                Q.tm_mod = g_tm_mod;
+                Q.skew = g_skew_a; Q.skew_mod = g_skew_mod_a;
                 { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, spA, Q, dim3(tA, g), hp.nthrA2, hp.smem_A2, st)); }
+                Q.skew = g_skew_b; Q.skew_mod = g_skew_mod_b;
                 { LaunchScope ls(4, st); CUDA_TRY(Long2Dispatch<T>::B(hp.cfgB, spB, Q, dim3(tB, g), hp.nthrB2, hp.smem_B2, st)); }
             }
             if (ns > 1)

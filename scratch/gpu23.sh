@@ -1,0 +1,19 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+run() {
+env "$@" timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_sweep.log 2>&1; python - <<PY
+import json
+l=[x for x in open('gpurun_out/bench_sweep.log') if x.startswith('{')]
+if not l: print("$*", 'FAILED', open('gpurun_out/bench_sweep.log').read()[-300:])
+else:
+    d=json.loads(l[-1]); c=d['config']; print("$*", ': ms/step %.2f rows/launch %d' % (d['ms_per_step'], c['rows_per_launch']), {k:(round(v['ms_sum_of_launches'],1)) for k,v in d['roofline']['classes'].items() if k.startswith('inv')})
+PY
+}
+run NWCWT_STREAMS=1 NWCWT_RING_MB=16
+run NWCWT_STREAMS=1 NWCWT_RING_MB=32
+run NWCWT_STREAMS=1 NWCWT_RING_MB=64
+run NWCWT_STREAMS=1 NWCWT_RING_MB=96
+run NWCWT_STREAMS=2 NWCWT_RING_MB=16
+run NWCWT_STREAMS=2 NWCWT_RING_MB=24
+run NWCWT_STREAMS=2 NWCWT_RING_MB=32
+run NWCWT_STREAMS=3 NWCWT_RING_MB=16

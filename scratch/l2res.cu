@@ -1,0 +1,64 @@
+// Does data written by one kernel stay in L2 for the next kernel on B200?  write N MB, then read it back; GB/s of the read.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cstdint>
+__global__ void wr(float4* p, size_t n, float v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = make_float4(v, v + 1, v + 2, v + 3);
+}
+__global__ void rd(const float4* p, size_t n, float* out) {
+    float acc = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { float4 a = p[i]; acc += a.x + a.y + a.z + a.w; }
+    if (acc == 123.456f) out[0] = acc;
+}
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void rd_bulk(const char* p, size_t bytes, float* out) {   // 32 KB bulk copies per CTA iteration
+    extern __shared__ __align__(128) char sm[];
+    uint64_t* bar = (uint64_t*)(sm + 32768);
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    uint32_t ph = 0; float acc = 0;
+    for (size_t off = (size_t)blockIdx.x * 32768; off + 32768 <= bytes; off += (size_t)gridDim.x * 32768) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(32768) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(sm)), "l"(p + off), "r"(32768), "r"(s32(bar)) : "memory");
+        }
+        asm volatile("{\n.reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}" ::"r"(s32(bar)), "r"(ph) : "memory");
+        ph ^= 1;
+        acc += ((float*)sm)[threadIdx.x];
+        __syncthreads();
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+int main() {
+    float* out; cudaMalloc(&out, 4);
+    char* buf; size_t maxb = (size_t)512 << 20; cudaMalloc(&buf, maxb);
+    char* trash; cudaMalloc(&trash, (size_t)512 << 20);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaFuncSetAttribute(rd_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 33024);
+    for (int mode = 0; mode < 3; ++mode)
+    for (size_t mb : {4, 8, 16, 24, 32, 48, 64, 96, 128, 256}) {
+        size_t bytes = mb << 20, n = bytes / 16;
+        float best = 1e9, bestc = 1e9;
+        for (int rep = 0; rep < 5; ++rep) {
+            // warm: write then read (L2 may hold it)
+            wr<<<148 * 8, 256>>>((float4*)buf, n, (float)rep);
+            cudaEventRecord(e0);
+            if (mode == 0) rd<<<148 * 8, 256>>>((const float4*)buf, n, out);
+            else if (mode == 1) rd_bulk<<<148 * 4, 128, 33024>>>(buf, bytes, out);
+            else { wr<<<148 * 8, 256>>>((float4*)buf, n, 1.f); }   // mode 2: re-write (write hit?)
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best;
+            // cold: trash L2 in between
+            wr<<<148 * 8, 256>>>((float4*)buf, n, (float)rep);
+            wr<<<148 * 8, 256>>>((float4*)trash, ((size_t)512 << 20) / 16, 2.f);
+            cudaEventRecord(e0);
+            if (mode == 0) rd<<<148 * 8, 256>>>((const float4*)buf, n, out);
+            else if (mode == 1) rd_bulk<<<148 * 4, 128, 33024>>>(buf, bytes, out);
+            else { wr<<<148 * 8, 256>>>((float4*)buf, n, 1.f); }
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1); bestc = ms < bestc ? ms : bestc;
+        }
+        printf("%s %4zu MB: after-write %.1f GB/s   after-trash %.1f GB/s\n", mode == 0 ? "LDG " : mode == 1 ? "bulk" : "rewr", mb, bytes / best / 1e6, bytes / bestc / 1e6);
+    }
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+}
