@@ -58,6 +58,15 @@ template <typename T, int R> NW_HD void tw_powers(cx<T> w, cx<T>* p) {
 
 template <typename T, int DIR> NW_HD cx<T> tw_dir(cx<T> w) { return DIR > 0 ? w : mk<T>(w.x, -w.y); }
 
+// w^r, r = 1..R-1, for w = tw[idx]: one table load, the powers by a product tree (depth log2 R).  A second table
+// seed (w^(R/2)) would halve the rounding error of the powers but was measured to DOUBLE the kernel times on B200:
+// its lane addresses are R/2 times further apart, and the kernels are bound by L1 / shared-memory wavefronts.
+template <typename T, int R, int DIR> NW_HD void tw_powers_tab(const cx<T>* NW_RESTRICT tw, int idx, cx<T>* p) {
+    p[1] = tw_dir<T, DIR>(tw[idx]);
+#pragma unroll
+    for (int r = 2; r < R; ++r) p[r] = cmul(p[r / 2], p[r - r / 2]);
+}
+
 // Geometry of one pass: P points, blocks of L = P / ns with Q = L / R butterflies each (= element
 // stride), twiddle table stride tws = ns, 2^tpsh lane pairs interleaved.  GeoDyn reads a run-time
 // plan; GeoStat is the same interface with everything a compile-time constant - used by the kernels
@@ -135,7 +144,7 @@ NW_HD void dif_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
             if (pk_lo(acc.re) == (T)123.456) e[0] = acc;
 #else
             cx<T> w[R];
-            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * g.tws]), w);
+            tw_powers_tab<T, R, DIR>(tw, np * g.tws, w);
             e[0] = v[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) e[r * stride] = cmul_s(v[r], w[r]);
@@ -250,7 +259,7 @@ NW_HD void dit_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
             }
         } else {
             cx<T> w[R];
-            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * g.tws]), w);
+            tw_powers_tab<T, R, DIR>(tw, np * g.tws, w);
             v[0] = e[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = cmul_s(e[r * stride], w[r]);
@@ -290,7 +299,8 @@ NW_HD void dit_stage_any(const Fft2Plan& st, int s, const SeqDesc& tpsh, const c
 }
 
 // No barrier on entry or exit: the caller orders buf's reuse and dst's visibility.
-template <typename T, int DIR, class Src, class Dst>
+// SKIP_FIRST: the caller has already run the first pass (radix[nst-1] on contiguous groups; nst >= 2) itself.
+template <typename T, int DIR, class Src, class Dst, bool SKIP_FIRST = false>
 NW_HD void fft2_dit(const Fft2Plan& st, const SeqDesc& sq, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Src& src,
                     const Dst& dst, int tid, int nthr) {
     const int m = st.nst;
@@ -298,7 +308,7 @@ NW_HD void fft2_dit(const Fft2Plan& st, const SeqDesc& sq, const cx<T>* NW_RESTR
         dit_stage_any<T, DIR, true, true>(st, 0, sq, tw, buf, src, dst, tid, nthr);
         return;
     }
-    dit_stage_any<T, DIR, true, false>(st, m - 1, sq, tw, buf, src, dst, tid, nthr);
+    if (!SKIP_FIRST) dit_stage_any<T, DIR, true, false>(st, m - 1, sq, tw, buf, src, dst, tid, nthr);
     NW_SYNC();
 #pragma unroll 1
     for (int s = m - 2; s >= 1; --s) {
@@ -315,15 +325,15 @@ NW_HD void fft2_dit(const Fft2Plan& st, int tpsh, const cx<T>* NW_RESTRICT tw, c
 
 // Compile-time plan P = R0 R1 R2 (radix order as in Fft2Plan: the first pass runs the LAST radix; R2 = 1:
 // two passes).  Input already in buf at its fft2_dit_pos slots.
-template <typename T, int DIR, int TPS, int P, int R0, int R1, int R2, class Dst>
+template <typename T, int DIR, int TPS, int P, int R0, int R1, int R2, class Dst, bool SKIP_FIRST = false>
 NW_HD void fft2_dit_static(const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const Dst& dst, int tid, int nthr) {
     const FromBuf src;
     if constexpr (R2 > 1) {
-        dit_body<T, (R2 > 1 ? R2 : 2), DIR, true, false>(GeoStat<P, R0 * R1, (R2 > 1 ? R2 : 2), TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
+        if (!SKIP_FIRST) dit_body<T, (R2 > 1 ? R2 : 2), DIR, true, false>(GeoStat<P, R0 * R1, (R2 > 1 ? R2 : 2), TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
         NW_SYNC();
         dit_body<T, R1, DIR, false, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
     } else {
-        dit_body<T, R1, DIR, true, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
+        if (!SKIP_FIRST) dit_body<T, R1, DIR, true, false>(GeoStat<P, R0, R1, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);
     }
     NW_SYNC();
     dit_body<T, R0, DIR, false, true>(GeoStat<P, 1, R0, TPS, RevNone>(), tw, buf, src, dst, tid, nthr);

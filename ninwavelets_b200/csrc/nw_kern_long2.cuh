@@ -22,7 +22,12 @@ template <> struct Cfg2<3> { static const int maxreg = 128; };              //  
 template <typename T, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2_kernel(const __grid_constant__ Long2Params<T> P) {
     extern __shared__ __align__(32) char nw_smem[];
-    passA2_body<T, SP>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+    passA2_body<T, SP, false>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+}
+template <typename T, int CFG, int SP>
+__global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2n_kernel(const __grid_constant__ Long2Params<T> P) {
+    extern __shared__ __align__(32) char nw_smem[];
+    passA2_body<T, SP, true>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
 template <typename T, int CFG>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2p_kernel(const __grid_constant__ Long2Params<T> P) {
@@ -46,6 +51,8 @@ __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passB2_kernel(const __grid_
 }
 
 template <typename T, int CFG, int SP> static cudaError_t prepA() {
+    cudaError_t e = cudaFuncSetAttribute(nwcwt_passA2n_kernel<T, CFG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(nwcwt_passA2_kernel<T, CFG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
 }
 template <typename T, int CFG, int SP> static cudaError_t prepB() {
@@ -57,7 +64,8 @@ template <typename T, int CFG, int SP> static cudaError_t prepB() {
     return cudaFuncSetAttribute(nwcwt_passB2_kernel<T, OUT_POWER, CFG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
 }
 template <typename T, int CFG, int SP> static cudaError_t runA(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
-    nwcwt_passA2_kernel<T, CFG, SP><<<grid, nthr, smem, s>>>(P);
+    if (P.narrow) nwcwt_passA2n_kernel<T, CFG, SP><<<grid, nthr, smem, s>>>(P);
+    else nwcwt_passA2_kernel<T, CFG, SP><<<grid, nthr, smem, s>>>(P);
     return cudaGetLastError();
 }
 template <typename T, int CFG, int SP> static cudaError_t runB(const Long2Params<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {

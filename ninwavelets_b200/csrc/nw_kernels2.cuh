@@ -38,6 +38,8 @@ struct Long2Params {
     const PrunePlan* pplans;   // pruned pass A: plans indexed by FreqRec::pad_
     int skew, skew_mod; // start-up stagger of the first wave: CTA waits ((linear block id / n_sm) % skew_mod) * skew cycles
     int n_sm;
+    int narrow;         // launch the narrow-band variant of pass A (host side only)
+    fastdiv dstepA;     // narrow-band pass A: x / (N1 / radix of the first pass)
     int tm_mod;         // timing experiment only: rows share Tm slots (by % tm_mod); 0 = off
     int row0;           // first row (signal-major: row = signal * F + frequency) of this launch
     int out_mode;
@@ -162,7 +164,8 @@ template <typename T> NW_HD size_t passB2_smem_bytes(int N2, int tpsh) { return 
 // The tile's input - spectrum x signal spectrum on the non-zero band only - is gathered into the
 // transform's shared-memory slots by a compact loop (one evaluation per in-band bin, nothing unrolled
 // around the formula), the rest of the tile is zero.
-template <typename T, int SP>
+// NARROW: the planner guarantees that every frequency's band touches at most N1 / R_last rows (HostPlan::narrowA).
+template <typename T, int SP, bool NARROW = false>
 NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
     cx2<T>* buf = (cx2<T>*)smem;
     const int tpsh = P.tpshA, TP = 1 << tpsh;
@@ -179,6 +182,43 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     if (k1hi > N1 - 1) k1hi = N1 - 1;
     const int nk1 = k1hi - k1lo + 1;
     first_wave_stagger<T>(P, bx, by, (N2 + 2 * TP - 1) / (2 * TP));
+    TmDst2<T> dst{&P, P.Tm + (size_t)(P.tm_mod > 0 ? by % P.tm_mod : by) * P.tm_stride, c, 1, fastdiv{1, 0}};
+    typedef StaticPlan<SP> S;
+    if constexpr (NARROW) {
+        // Narrow band (it touches at most N1 / R rows): every butterfly of the first pass - inputs k1 = rev + q * step -
+        // has at most ONE non-zero input, so the pass needs no zero fill, no gather and no loads: evaluate that one
+        // product y = W_f(k) X[k] (if any) and write its R outputs  y * (w_R^q)^j,  j = 0..R-1.
+        const int rl = P.stA.radix[P.stA.nst - 1], step = N1 / rl;
+        for (int i = tid; i < (step << tpsh); i += nthr) {
+            const int tp = i & (TP - 1);
+            const int blk = i >> tpsh;
+            const int rev = fft2_rev(P.stA, blk);
+            const int q = rev >= k1lo ? 0 : (int)fd_div((uint32_t)(k1lo - rev + step - 1), P.dstepA);
+            const int k1 = rev + q * step;
+            const int k2 = c + 2 * tp;
+            cx2<T>* e = buf + (((size_t)blk * rl) << tpsh) + tp;
+            const bool ok = nk1 > 0 && q < rl && k1 <= k1hi;
+            cx2<T> y = zero2<T>();
+            cx<T> wq = mk<T>((T)1, (T)0);
+            if (ok) {
+                const int k = k1 * N2 + k2;
+                cx<T> a = mk<T>((T)0, (T)0), b = a;
+                if (k2 < N2 && k >= rec.lo && k < rec.hi) a = spec_times<T>(P.sp, rec, fi, k, X[k]);
+                if (k2 + 1 < N2 && k + 1 >= rec.lo && k + 1 < rec.hi) b = spec_times<T>(P.sp, rec, fi, k + 1, X[k + 1]);
+                y = mk2<T>(a, b);
+                wq = P.twA[q * step];
+            }
+            e[0] = y;
+#pragma unroll 4
+            for (int j = 1; j < rl; ++j) {
+                y = cmul_s(y, wq);
+                e[(size_t)j << tpsh] = y;
+            }
+        }
+        if constexpr (SP == 0) fft2_dit<T, +1, FromBuf, TmDst2<T>, true>(P.stA, seq_pow2(tpsh), P.twA, buf, FromBuf(), dst, tid, nthr);
+        else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2, TmDst2<T>, true>(P.twA, buf, dst, tid, nthr);
+        return;
+    }
     const cx2<T> z = zero2<T>();
     for (int i = tid; i < (N1 << tpsh); i += nthr) buf[i] = z;
     NW_SYNC();
@@ -193,8 +233,6 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(a, b);
     }
     NW_SYNC();
-    TmDst2<T> dst{&P, P.Tm + (size_t)(P.tm_mod > 0 ? by % P.tm_mod : by) * P.tm_stride, c, 1, fastdiv{1, 0}};
-    typedef StaticPlan<SP> S;
     if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
     else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twA, buf, dst, tid, nthr);
 }

@@ -58,6 +58,7 @@ struct HostPlan {
     int nthrA2 = 256, nthrB2 = 256;
     int cfgA = 0, cfgB = 0;      // compiled launch shape (CFG2_*) of each pass
     int generic_ok = 1;          // long path: the generic two-pass kernels also have a plan for this N
+    int narrowA = 0;             // every band touches <= N1 / R_last rows: pass A's first pass needs no loads (nw_kernels2.cuh)
     int pruneA = 0;              // pass A runs the pruned kernel (per-frequency PrunePlan, FreqRec::pad_)
     std::vector<PrunePlan> pplans;
     size_t smem_A2 = 0, smem_B2 = 0;
@@ -368,6 +369,18 @@ inline int env_int(const char* name, int dflt);
 inline void plan_prune(HostPlan& hp) {
     hp.pruneA = 0;
     hp.pplans.clear();
+    hp.narrowA = 0;
+    if (hp.fast && hp.F > 0 && hp.stA2.nst >= 2 && !env_int("NWCWT_NO_NARROW", 0)) {
+        const int step = hp.N1f / hp.stA2.radix[hp.stA2.nst - 1];
+        int worst = 0;
+        for (int i = 0; i < hp.F; ++i) {
+            const FreqRec& r = hp.rec[i];
+            // rows a tile of 2 << tpshA columns can touch: one more than the band's own row span
+            const int C = r.hi > r.lo ? (r.hi - 1) / hp.N2f - r.lo / hp.N2f + 2 : 0;
+            worst = std::max(worst, C);
+        }
+        hp.narrowA = worst <= step;
+    }
     // r01 measurement (profiles/r01/shape_sweep.md): with run-time plans the pruned kernel executes as many
     // instructions as the unpruned compile-time-plan kernel and stalls on its phase-table loads (22.6 vs
     // 15.4 ms per cfg2 step), so it is opt-in (NWCWT_PRUNE=1) until it has compile-time plans of its own.

@@ -255,7 +255,9 @@ static int ensure_device_t(nwcwt_plan* pl) {
         if (hp.fast) {
             CUDA_TRY(Long2Dispatch<T>::prepare(hp.cfgA));
             CUDA_TRY(Long2Dispatch<T>::prepare(hp.cfgB));
-            if (!getenv("NWCWT_NO_L2_PERSIST")) {
+            // measured (profiles/r01/shape_sweep.md): an L2 persistence window on the Tm ring makes the step
+            // slower (24.2-26.3 vs 23.3 ms), so it is opt-in for experiments only
+            if (getenv("NWCWT_L2_PERSIST")) {
                 int v = 0;
                 cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, hp.device);
                 pl->l2_persist_max = (size_t)(v > 0 ? v : 0);
@@ -531,6 +533,8 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
                 Q.Tm = Tm + (size_t)slot * (size_t)hp.ring2 * (size_t)hp.tm_stride2;
                 Q.n_sm = device_sms(hp.device);
                 Q.tm_mod = g_tm_mod;
+                Q.narrow = hp.narrowA;
+                if (hp.stA2.nst >= 1) Q.dstepA = make_fastdiv((uint32_t)std::max(1, hp.N1f / hp.stA2.radix[hp.stA2.nst - 1]));
                 Q.skew = g_skew_a; Q.skew_mod = g_skew_mod_a;
                 { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, spA, Q, dim3(tA, g), hp.nthrA2, hp.smem_A2, st)); }
                 Q.skew = g_skew_b; Q.skew_mod = g_skew_mod_b;

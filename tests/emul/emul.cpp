@@ -198,17 +198,21 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
             const int ntA = (g_mode & 4) ? 1 : hp.nthrA2, ntB = (g_mode & 4) ? 1 : hp.nthrB2;
             const long long rows = (long long)gs * hp.F;
             Q.pplans = hp.pplans.data();
+            if (hp.stA2.nst >= 1) Q.dstepA = make_fastdiv((uint32_t)std::max(1, hp.N1f / hp.stA2.radix[hp.stA2.nst - 1]));
             const int spA = (hp.pruneA && !(g_mode & 16)) ? -1 : (g_mode & 8) ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = (g_mode & 8) ? 0 : static_plan_id(hp.stB2, hp.tpshB);
             for (long long r0 = 0; r0 < rows; r0 += ring2) {
                 const int g = (int)std::min<long long>(ring2, rows - r0);
                 Q.row0 = (int)r0;
                 for (int y = 0; y < g; ++y) for (int x = 0; x < tA; ++x)
                     Fibers::get().run(ntA, [&](int t) {
-                        switch (spA) {
-                            case -1: passA2p_body<T>(Q, smp, x, y, t, ntA); break;
-                            case 2: passA2_body<T, 2>(Q, smp, x, y, t, ntA); break;
-                            case 4: passA2_body<T, 4>(Q, smp, x, y, t, ntA); break;
-                            default: passA2_body<T, 0>(Q, smp, x, y, t, ntA); break;
+                        if (spA == -1) passA2p_body<T>(Q, smp, x, y, t, ntA);
+                        else if (hp.narrowA && !(g_mode & 64)) {
+                            if (spA == 2) passA2_body<T, 2, true>(Q, smp, x, y, t, ntA);
+                            else passA2_body<T, 0, true>(Q, smp, x, y, t, ntA);
+                        } else {
+                            if (spA == 2) passA2_body<T, 2>(Q, smp, x, y, t, ntA);
+                            else if (spA == 4) passA2_body<T, 4>(Q, smp, x, y, t, ntA);
+                            else passA2_body<T, 0>(Q, smp, x, y, t, ntA);
                         }
                     });
                 for (int y = 0; y < g; ++y) for (int x = 0; x < tB; ++x)

@@ -1,7 +1,7 @@
 #include <stdio.h>
 #include <complex>
 #include <vector>
-#include "../ninwavelets_b200/csrc/nw_bfly2.cuh"
+#include "../../ninwavelets_b200/csrc/nw_bfly2.cuh"
 using namespace nw;
 template <typename T, int R, int DIR> double test() {
     cx2<T> v[R];

@@ -1,8 +1,8 @@
 #include <stdio.h>
 #include <complex>
 #include <vector>
-#include "../ninwavelets_b200/csrc/nw_fft2.cuh"
-#include "../ninwavelets_b200/csrc/nw_plan.h"
+#include "../../ninwavelets_b200/csrc/nw_fft2.cuh"
+#include "../../ninwavelets_b200/csrc/nw_plan.h"
 using namespace nw;
 typedef std::complex<double> cd;
 template <typename T> struct VecSrc { const cd* x; int P; int TT;   // x[t*P + p]

@@ -64,11 +64,11 @@ def test_emul_long_path_forced(golden_transforms, name, dtype):
         assert l2_rel_err(z.astype(np.complex128), ref).max() <= F32_TOL
 
 
-@pytest.mark.parametrize("flags", [1, 1 | 16, 1 | 8 | 16, 1 | 2, 1 | 4, 1 | 32])
+@pytest.mark.parametrize("flags", [1, 1 | 16, 1 | 8 | 16, 1 | 2, 1 | 4, 1 | 32, 1 | 16 | 64])
 def test_emul_long_path_variants_agree(flags):
     """Same input through every variant of the long path: pruned pass A (default), unpruned compile-time or
     run-time plans (16, 8|16), generic kernels (2), one stepping thread instead of fibers (4), generic forward
-    transform under the packed inverse (32)."""
+    transform under the packed inverse (32), no narrow-band first pass (64; 16 alone runs it where the plan allows)."""
     rng = np.random.default_rng(11)
     for kind, kw, n, freqs in (("morse", {}, 6000, np.array([1., 2.5, 9., 30., 77., 210., 499.])),
                                 ("morlet", dict(sigma=7.0), 3600, np.arange(1., 60., 7.)),
