@@ -290,7 +290,7 @@ def run_graft(args, wl):
         "algorithmic_bytes_per_step": alg_bytes_step,
         "kernel_ms_per_step": step_ms,
         "avg_launch_ms": step_ms / max(n_launch, 1),
-        "fp32_lane_rate_note": "see DESIGN.md: the kernels are bound by the FP32 pipe, not by HBM",
+        "note": "DESIGN.md section 5: the kernels are bound by shared-memory/L1 wavefronts and FP32 lane rate, not by HBM",
         "classes": {k: {"ms_sum_of_launches": round(v["ms"], 4), "launches": v["launches"], "share": v["ms"] / tot_ms,
                         "avg_launch_ms": v["ms"] / v["launches"]} for k, v in kern.items()},
     }
@@ -361,7 +361,7 @@ def run_graft(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
