@@ -264,7 +264,9 @@ NW_HD void dit_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = cmul_s(e[r * stride], w[r]);
         }
+#if !defined(NW_KNOCKOUT) || NW_KNOCKOUT != 5   /* 5: timing experiment, no butterflies in the DIT passes */
         B2<T, R, DIR>::run(v);
+#endif
         if (LAST) {
             dst.template store_all<R>(ctx, v);
         } else {

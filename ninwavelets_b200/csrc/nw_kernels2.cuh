@@ -124,8 +124,13 @@ template <typename T, int DIR = 1> struct TmDst2 {
         x.two = k2 + 1 < N2;
         const int k2a = x.valid ? k2 : 0, k2b = x.two ? k2 + 1 : k2a;
         const int n1 = a + n1a * base, dn1 = n1a * step;
+#if defined(NW_KNOCKOUT) && NW_KNOCKOUT == 4   /* timing experiment: no twiddle-table look-ups */
+        x.cur = mk2<T>(mk<T>((T)1, (T)(k2a * n1)), mk<T>((T)1, (T)0));
+        x.g = mk2<T>(mk<T>((T)1, (T)dn1), mk<T>((T)1, (T)0));
+#else
         x.cur = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * n1), big_twiddle2<T, DIR>(*P, k2b * n1));
         x.g = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * dn1), big_twiddle2<T, DIR>(*P, k2b * dn1));
+#endif
         x.col = tm + ((size_t)k2a << (P->tpshB + 1));
         x.n1 = (uint32_t)n1;
         x.step = (uint32_t)dn1;
@@ -144,16 +149,26 @@ template <typename T, int DIR = 1> struct TmDst2 {
         for (int q = 0; q < R; ++q, n1 += x.step) {
             const cx2<T> y = cmul_p(v[q], cur[q & 1]);
             if (q + 2 < R) cur[q & 1] = cmul_p(cur[q & 1], g2);
-            // Tm holds lane-packed units {re(n1), re(n1+1), im(n1), im(n1+1)} per (k2, row pair): pass B's tile needs no
-            // repacking, and the four scalars go out straight from the packed registers
+            // Tm holds plain complex values, TB consecutive rows n1 of one column contiguous.  (-DNW_TM_PACKED: lane-packed
+            // units {re(n1), re(n1+1), im(n1), im(n1+1)} written as four scalars - no repacking in pass B but twice the
+            // store sectors; measured 2.6 % slower per cfg2 step.)
             const size_t e = (size_t)((n1 >> shB) * blk + (n1 & mask));          // complex index within the column pair's rows
             T* o = (T*)x.col + (((e >> 1) << 2) + (n1 & 1u));
+#if defined(NW_KNOCKOUT) && NW_KNOCKOUT == 3   /* timing experiment: no Tm stores */
+            if (pk_lo(y.re) != (T)123.456) continue;
+#endif
+#if !defined(NW_TM_PACKED)   /* plain complex Tm: 8-byte stores that fill whole sectors; pass B repacks in its first pass */
+            cx<T>* oc = x.col + e;
+            oc[0] = lane0(y);
+            if (x.two) oc[(size_t)1 << shB] = lane1(y);
+#else
             o[0] = pk_lo(y.re);
             o[2] = pk_lo(y.im);
             if (x.two) {
                 o[(size_t)2 << shB] = pk_hi(y.re);
                 o[((size_t)2 << shB) + 2] = pk_hi(y.im);
             }
+#endif
         }
     }
 };
@@ -400,8 +415,13 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
     LongOutDst2<T, MODE> dst{(char*)P.out + (size_t)gr * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
     typedef StaticPlan<SP> S;
-    if constexpr (SP == 0) fft2_dif<T, DIR, false>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
-    else fft2_dif_static<T, DIR, false, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
+#if !defined(NW_TM_PACKED)
+    constexpr bool RAWT = true;
+#else
+    constexpr bool RAWT = false;
+#endif
+    if constexpr (SP == 0) fft2_dif<T, DIR, RAWT>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
+    else fft2_dif_static<T, DIR, RAWT, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
 }
 
 }  // namespace nw
