@@ -298,3 +298,25 @@ def test_2_26_properties(nw):
         lhs = float((za[i].real.double() ** 2 + za[i].imag.double() ** 2).sum())
         rhs = float(((W * X).abs() ** 2).sum()) / n
         assert abs(lhs - rhs) / rhs <= 100 * F32_TOL
+
+
+@pytest.mark.parametrize("n", [50625, 56250, 57344, 98304, 30375, 20000, 16384 + 8192])
+def test_awkward_long_lengths(nw, n):
+    """Odd N1 (unaligned output pairs), partial row tiles, a factor 7 (generic kernels), mixed 2-3-5 lengths: every long-row
+    variant against the oracle in fp64 and fp32, cwt and power with a Baseline epilogue."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n))
+    fr = np.array([2.0, 17.0, 140.0])
+    fam = orc.Family("morlet", sfreq=1000, sigma=7.)
+    ref = np.stack([orc.cwt(fam, xi, fr) for xi in x])
+    z = make(nw, "morlet", dict(sfreq=1000, sigma=7.), dtype="float64").cwt(x, fr)
+    assert peak_rel_err(z.reshape(-1, n), ref.reshape(-1, n)).max() <= F64_TOL, n
+    x32 = x.astype(np.float32)
+    refp = np.stack([orc.baseline_rows(orc.power(fam, xi.astype(np.float64), fr), 1000., 0.1, 0.9, "zscore") for xi in x32])
+    p = make(nw, "morlet", dict(sfreq=1000, sigma=7.), dtype="float32").power(x32, fr, baseline=("zscore", 0.1, 0.9))
+    assert l2_rel_err(p.reshape(-1, n).astype(np.float64), refp.reshape(-1, n)).max() <= 3 * F32_TOL, n
+
+
+def test_unsupported_length_raises(nw):
+    with pytest.raises(Exception):
+        make(nw, "morse", dict(sfreq=1000), dtype="float32").power(np.zeros(100003, dtype=np.float32), [1.0, 2.0])
