@@ -280,8 +280,19 @@ def run_graft(args, wl):
     step_ms = ms / args.steps
     achieved = alg_bytes_step / (step_ms * 1e-3) / 1e9
     n_launch = sum(v["launches"] for v in kern.values())
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01", "traffic_%s.json" % args.workload)
+    if os.path.isfile(tpath) and f32:
+        try:
+            tj = json.load(open(tpath))
+            pairs = (S * F) / float(tj["rows_per_launch"])
+            traffic = (tj["passA_bytes_per_launch"] + tj["passB_bytes_per_launch"]) * pairs
+            traffic_note = "DRAM bytes per step from the committed ncu capture (%s); %s" % (tj["source"], tj["note"])
+        except Exception:
+            traffic = None
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_note": traffic_note,
         "peak_source": peak_src,
         "kernel": "all kernels of one step (%s); dominant class %s" % (
             "one fused kernel" if info["path"] == "short" else
