@@ -164,4 +164,71 @@ template <typename T, int DIR> struct B2<T, 16, DIR> {
     }
 };
 
+// ---- generic Cooley-Tukey composition R = RA * RB with compile-time twiddles ----------------
+//   n = RB n1 + n2,  k = k1 + RA k2:   X[k] = sum_n2 w_RB^{n2 k2} [ w_R^{n2 k1} sum_n1 x[n] w_RA^{n1 k1} ]
+// cos / sin of 2 pi j / R evaluated at compile time (Taylor series on the first octant).
+constexpr double ct_pi = 3.14159265358979323846264338327950288;
+constexpr double ct_cos_small(double x) {   // |x| <= pi/4
+    double t = 1, sum = 1;
+    for (int i = 1; i <= 12; ++i) { t *= -x * x / ((2 * i - 1) * (2 * i)); sum += t; }
+    return sum;
+}
+constexpr double ct_sin_small(double x) {
+    double t = x, sum = x;
+    for (int i = 1; i <= 12; ++i) { t *= -x * x / ((2 * i) * (2 * i + 1)); sum += t; }
+    return sum;
+}
+// cos(2 pi j / R), j in [0, R)
+constexpr double ct_cos(int j, int R) {
+    j %= R;
+    if (2 * j > R) j = R - j;                              // cos is even around pi
+    if (4 * j > R) return -ct_cos(R - 2 * j, 2 * R);       // cos(x) = -cos(pi - x); (R - 2j)/(2R) turns
+    if (8 * j > R) return ct_sin_small(2 * ct_pi * (R - 4 * j) / (4.0 * R));   // cos(x) = sin(pi/2 - x)
+    return ct_cos_small(2 * ct_pi * j / R);
+}
+constexpr double ct_sin(int j, int R) {   // sin(x) = cos(x - pi/2) = cos(2 pi (4j - R) / (4R))
+    return ct_cos(((4 * j - R) % (4 * R) + 4 * R) % (4 * R), 4 * R);
+}
+template <int R> struct CtTab {
+    double c[R], s[R];
+    constexpr CtTab() : c(), s() {
+        for (int j = 0; j < R; ++j) { c[j] = ct_cos(j, R); s[j] = ct_sin(j, R); }
+    }
+};
+
+template <typename T, int RA, int RB, int DIR> struct CtB2 {
+    static NW_HD void run(cx2<T>* v) {
+        constexpr int R = RA * RB;
+        constexpr CtTab<R> tab{};
+        cx2<T> u[R];   // u[k1 * RB + n2]
+#pragma unroll
+        for (int n2 = 0; n2 < RB; ++n2) {
+            cx2<T> t[RA];
+#pragma unroll
+            for (int n1 = 0; n1 < RA; ++n1) t[n1] = v[RB * n1 + n2];
+            B2<T, RA, DIR>::run(t);
+#pragma unroll
+            for (int k1 = 0; k1 < RA; ++k1) {
+                const int j = (k1 * n2) % R;
+                if (j == 0) u[k1 * RB + n2] = t[k1];
+                else if (4 * j == R) u[k1 * RB + n2] = rot2<DIR, T>(t[k1]);
+                else u[k1 * RB + n2] = cmul_k<DIR, T>(t[k1], (T)tab.c[j], (T)tab.s[j]);
+            }
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < RA; ++k1) {
+            cx2<T> t[RB];
+#pragma unroll
+            for (int n2 = 0; n2 < RB; ++n2) t[n2] = u[k1 * RB + n2];
+            B2<T, RB, DIR>::run(t);
+#pragma unroll
+            for (int k2 = 0; k2 < RB; ++k2) v[k1 + RA * k2] = t[k2];
+        }
+    }
+};
+template <typename T, int DIR> struct B2<T, 25, DIR> : CtB2<T, 5, 5, DIR> {};
+template <typename T, int DIR> struct B2<T, 32, DIR> : CtB2<T, 4, 8, DIR> {};
+template <typename T, int DIR> struct B2<T, 24, DIR> : PfaB2<T, 3, 8, DIR> {};
+template <typename T, int DIR> struct B2<T, 30, DIR> : PfaB2<T, 5, 6, DIR> {};
+
 }  // namespace nw

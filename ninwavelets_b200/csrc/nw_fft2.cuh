@@ -173,6 +173,11 @@ NW_HD void dif_stage_any(const Fft2Plan& st, int s, const SeqDesc& tpsh, const c
         case 12: dif_stage<T, 12, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
         case 15: dif_stage<T, 15, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
         case 16: dif_stage<T, 16, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+#ifdef NW_BIG_RADIX
+        case 25: dif_stage<T, 25, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 30: dif_stage<T, 30, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+        case 32: dif_stage<T, 32, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
+#endif
         default: break;
     }
 }
@@ -296,6 +301,11 @@ NW_HD void dit_stage_any(const Fft2Plan& st, int s, const SeqDesc& tpsh, const c
         case 12: dit_stage<T, 12, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
         case 15: dit_stage<T, 15, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
         case 16: dit_stage<T, 16, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+#ifdef NW_BIG_RADIX
+        case 25: dit_stage<T, 25, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 30: dit_stage<T, 30, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+        case 32: dit_stage<T, 32, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
+#endif
         default: break;
     }
 }

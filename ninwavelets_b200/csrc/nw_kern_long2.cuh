@@ -18,6 +18,8 @@ template <> struct Cfg2<0> { static const int maxreg = NW_CFG0_MAXREG; };   // 2
 template <> struct Cfg2<1> { static const int maxreg = 96; };               // 224 x 3
 template <> struct Cfg2<2> { static const int maxreg = 96; };               // 128 x 5
 template <> struct Cfg2<3> { static const int maxreg = 128; };              //  64 x 8
+template <> struct Cfg2<4> { static const int maxreg = 255; };              // 128 x 2  (radix 25-32 plans)
+template <> struct Cfg2<5> { static const int maxreg = 168; };              // 128 x 3
 
 template <typename T, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2_kernel(const __grid_constant__ Long2Params<T> P) {

@@ -55,7 +55,12 @@ template <> struct StaticPlan<4> { static const int P = 256, R0 = 16, R1 = 16, R
 template <> struct StaticPlan<5> { static const int P = 512, R0 = 16, R1 = 8, R2 = 4, TPS = 2; };
 template <> struct StaticPlan<6> { static const int P = 1500, R0 = 10, R1 = 10, R2 = 15, TPS = 1; };   // short rows, cfg3
 template <> struct StaticPlan<7> { static const int P = 300, R0 = 12, R1 = 5, R2 = 5, TPS = 3; };      // short rows, cfg1
-static const int N_STATIC_PLANS = 7;
+// two-pass plans with radix 25-32 butterflies (launch shapes 4 and 5, NW_BIG_RADIX translation units)
+template <> struct StaticPlan<8> { static const int P = 1024, R0 = 32, R1 = 32, R2 = 1, TPS = 2; };
+template <> struct StaticPlan<9> { static const int P = 960, R0 = 32, R1 = 30, R2 = 1, TPS = 2; };
+template <> struct StaticPlan<10> { static const int P = 800, R0 = 32, R1 = 25, R2 = 1, TPS = 2; };
+template <> struct StaticPlan<11> { static const int P = 625, R0 = 25, R1 = 25, R2 = 1, TPS = 2; };
+static const int N_STATIC_PLANS = 11;
 template <int ID> NW_HD bool static_plan_matches(const Fft2Plan& st, int tpsh) {
     typedef StaticPlan<ID> S;
     if (st.P != S::P || tpsh != S::TPS) return false;
@@ -71,6 +76,10 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     if (static_plan_matches<5>(st, tpsh)) return 5;
     if (static_plan_matches<6>(st, tpsh)) return 6;
     if (static_plan_matches<7>(st, tpsh)) return 7;
+    if (static_plan_matches<8>(st, tpsh)) return 8;
+    if (static_plan_matches<9>(st, tpsh)) return 9;
+    if (static_plan_matches<10>(st, tpsh)) return 10;
+    if (static_plan_matches<11>(st, tpsh)) return 11;
     return 0;
 }
 

@@ -112,6 +112,34 @@ inline bool factorise(long long P, FftStages& st, std::string& err) {
 // one round trip of the tile through shared memory), then least butterfly arithmetic per point.
 // An odd radix, when there is one, goes last: the stride-1 pass then reads R-element groups whose
 // shared-memory footprint is conflict free for two butterflies per quarter warp.
+inline void fill_plan2(long long P, const std::vector<int>& rad, Fft2Plan& out) {
+    out.P = (int)P;
+    out.nst = (int)rad.size();
+    int ns = 1;
+    for (int i = 0; i < out.nst; ++i) {
+        out.radix[i] = rad[i];
+        out.ns[i] = ns;
+        const int L = (int)(P / ns);
+        out.div_q[i] = make_fastdiv((uint32_t)(L / rad[i]));
+        out.div_r[i] = make_fastdiv((uint32_t)rad[i]);
+        ns *= rad[i];
+    }
+}
+
+inline int env_int(const char* name, int dflt);
+
+// Two-pass plans with radix 24-32 butterflies (compile-time plans only, kernels of launch shapes 4 and 5);
+// opt-in: NWCWT_BIG bit 0 = pass B, bit 1 = pass A.
+inline bool plan_big(long long P, Fft2Plan& out) {
+    switch (P) {
+        case 1024: fill_plan2(P, {32, 32}, out); return true;
+        case 960: fill_plan2(P, {32, 30}, out); return true;
+        case 800: fill_plan2(P, {32, 25}, out); return true;
+        case 625: fill_plan2(P, {25, 25}, out); return true;
+        default: return false;
+    }
+}
+
 inline bool plan_packed(long long P, Fft2Plan& out) {
     if (P < 2 || P > (1 << 16)) return false;
     int e[3] = {0, 0, 0};
@@ -157,17 +185,7 @@ inline bool plan_packed(long long P, Fft2Plan& out) {
     std::sort(rad.begin(), rad.end(), [](int x, int y) { return x > y; });
     for (size_t i = 0; i < rad.size(); ++i)
         if (rad[i] & 1) { std::swap(rad[i], rad.back()); break; }   // one odd radix last
-    out.P = (int)P;
-    out.nst = (int)rad.size();
-    int ns = 1;
-    for (int i = 0; i < out.nst; ++i) {
-        out.radix[i] = rad[i];
-        out.ns[i] = ns;
-        const int L = (int)(P / ns);
-        out.div_q[i] = make_fastdiv((uint32_t)(L / rad[i]));
-        out.div_r[i] = make_fastdiv((uint32_t)rad[i]);
-        ns *= rad[i];
-    }
+    fill_plan2(P, rad, out);
     return true;
 }
 
@@ -324,10 +342,10 @@ inline int ilog2_floor(long long v) { int l = 0; while ((1LL << (l + 1)) <= v) +
 // take the multiple of 32 that wastes the fewest thread slots over all stages, weighted by how many
 // threads the shape keeps resident per SM (shared memory and registers), with a small bonus for the
 // shape with more registers per thread.
-static const int N_CFG2 = 4;
-static const int CFG2_MAXTHR[N_CFG2] = {256, 224, 128, 64};
-static const int CFG2_MINCTA[N_CFG2] = {3, 3, 5, 8};
-static const int CFG2_MAXREG[N_CFG2] = {80, 96, 96, 128};   // __maxnreg__ of the compiled kernels
+static const int N_CFG2 = 6;
+static const int CFG2_MAXTHR[N_CFG2] = {256, 224, 128, 64, 128, 128};
+static const int CFG2_MINCTA[N_CFG2] = {3, 3, 5, 8, 2, 3};
+static const int CFG2_MAXREG[N_CFG2] = {80, 96, 96, 128, 255, 168};   // __maxnreg__ of the compiled kernels
 inline int cfg2_regcap(int c) { return CFG2_MAXREG[c]; }
 
 inline void pick_threads2(const Fft2Plan& st, int tpsh, size_t smem, int ncfg, int& nthr, int& cfg) {
@@ -439,6 +457,8 @@ inline void plan_shape_fast(HostPlan& hp) {
             if (env_int("NWCWT_SPLIT_N1", 0) > 0 && n1 != env_int("NWCWT_SPLIT_N1", 0)) continue;   // tuning override
             Fft2Plan a, b;
             if (!plan_packed(n1, a) || !plan_packed(n2, b)) continue;
+            if (env_int("NWCWT_BIG", 0) & 2) plan_big(n1, a);
+            if (env_int("NWCWT_BIG", 0) & 1) plan_big(n2, b);
             const int fa = env_int("NWCWT_TPSH_A", -1), fb = env_int("NWCWT_TPSH_B", -1);   // tuning overrides
             for (int ta = 2; ta >= 0; --ta)
                 for (int tb = 2; tb >= 0; --tb) {
@@ -463,7 +483,7 @@ inline void plan_shape_fast(HostPlan& hp) {
         }
     }
     if (!hp.fast) return;
-    const int ncfg = hp.dtype == 0 ? N_CFG2 : 1;   // fp64 kernels exist in shape 0 only
+    const int ncfg = hp.dtype == 0 ? 4 : 1;   // fp64 kernels exist in shape 0 only; shapes 4, 5 are opt-in
     pick_threads2(hp.stA2, hp.tpshA, hp.smem_A2, ncfg, hp.nthrA2, hp.cfgA);
     pick_threads2(hp.stB2, hp.tpshB, hp.smem_B2, ncfg, hp.nthrB2, hp.cfgB);
     if (hp.dtype == 0) {   // tuning overrides (fp32 shapes only)
@@ -472,6 +492,12 @@ inline void plan_shape_fast(HostPlan& hp) {
         hp.cfgA = env_int("NWCWT_CFG_A", hp.cfgA);
         hp.cfgB = env_int("NWCWT_CFG_B", hp.cfgB);
     }
+    // radix 25-32 plans exist in the launch shapes 4 and 5 only (128 threads, 2 or 3 CTAs per SM)
+    auto big = [](const Fft2Plan& p) { for (int i = 0; i < p.nst; ++i) if (p.radix[i] > 20) return true; return false; };
+    if (big(hp.stA2) && hp.cfgA < 4) hp.cfgA = 5;
+    if (big(hp.stB2) && hp.cfgB < 4) hp.cfgB = 5;
+    if (hp.cfgA >= 4) hp.nthrA2 = std::min(hp.nthrA2, CFG2_MAXTHR[hp.cfgA]);
+    if (hp.cfgB >= 4) hp.nthrB2 = std::min(hp.nthrB2, CFG2_MAXTHR[hp.cfgB]);
     const int TB = 2 << hp.tpshB;
     const long long nblk = (hp.N1f + TB - 1) / TB;
     hp.tm_stride2 = nblk * hp.N2f * TB;

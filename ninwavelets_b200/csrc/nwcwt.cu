@@ -167,23 +167,18 @@ static void fill_twiddles(std::vector<cx<T>>& v, long long count, long long P, l
 
 // fast long path: compiled launch shapes and compile-time plans per precision (k_long2_*.cu)
 template <typename T> struct Long2Dispatch;
-#define NW_BY_CFG(c, expr0, expr1, expr2, expr3) \
-    switch (c) { case 1: return expr1; case 2: return expr2; case 3: return expr3; default: return expr0; }
+#define NW_BY_CFG(c, F, ...) \
+    switch (c) { case 1: return F<float, 1>(__VA_ARGS__); case 2: return F<float, 2>(__VA_ARGS__); \
+                 case 3: return F<float, 3>(__VA_ARGS__); case 4: return F<float, 4>(__VA_ARGS__); \
+                 case 5: return F<float, 5>(__VA_ARGS__); default: return F<float, 0>(__VA_ARGS__); }
 template <> struct Long2Dispatch<float> {
-    static cudaError_t prepare(int c) {
-        NW_BY_CFG(c, (prepare_long2<float, 0>()), (prepare_long2<float, 1>()), (prepare_long2<float, 2>()), (prepare_long2<float, 3>()))
-    }
-    static bool has(int c, int pass, int sp) {
-        NW_BY_CFG(c, (has_static_plan<float, 0>(pass, sp)), (has_static_plan<float, 1>(pass, sp)),
-                  (has_static_plan<float, 2>(pass, sp)), (has_static_plan<float, 3>(pass, sp)))
-    }
+    static cudaError_t prepare(int c) { NW_BY_CFG(c, prepare_long2) }
+    static bool has(int c, int pass, int sp) { NW_BY_CFG(c, has_static_plan, pass, sp) }
     static cudaError_t A(int c, int sp, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
-        NW_BY_CFG(c, (launch_passA2<float, 0>(sp, P, g, nt, sm, s)), (launch_passA2<float, 1>(sp, P, g, nt, sm, s)),
-                  (launch_passA2<float, 2>(sp, P, g, nt, sm, s)), (launch_passA2<float, 3>(sp, P, g, nt, sm, s)))
+        NW_BY_CFG(c, launch_passA2, sp, P, g, nt, sm, s)
     }
     static cudaError_t B(int c, int sp, const Long2Params<float>& P, dim3 g, int nt, size_t sm, cudaStream_t s) {
-        NW_BY_CFG(c, (launch_passB2<float, 0>(sp, P, g, nt, sm, s)), (launch_passB2<float, 1>(sp, P, g, nt, sm, s)),
-                  (launch_passB2<float, 2>(sp, P, g, nt, sm, s)), (launch_passB2<float, 3>(sp, P, g, nt, sm, s)))
+        NW_BY_CFG(c, launch_passB2, sp, P, g, nt, sm, s)
     }
 };
 template <> struct Long2Dispatch<double> {

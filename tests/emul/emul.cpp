@@ -212,12 +212,13 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
                         } else {
                             if (spA == 2) passA2_body<T, 2>(Q, smp, x, y, t, ntA);
                             else if (spA == 4) passA2_body<T, 4>(Q, smp, x, y, t, ntA);
+                            else if (spA == 11) passA2_body<T, 11>(Q, smp, x, y, t, ntA);
                             else passA2_body<T, 0>(Q, smp, x, y, t, ntA);
                         }
                     });
                 for (int y = 0; y < g; ++y) for (int x = 0; x < tB; ++x)
                     Fibers::get().run(ntB, [&](int t) {
-                        if (output == OUT_POWER) { if (spB == 1) passB2_body<T, OUT_POWER, 1>(Q, smp, x, y, t, ntB); else if (spB == 4) passB2_body<T, OUT_POWER, 4>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_POWER, 0>(Q, smp, x, y, t, ntB); }
+                        if (output == OUT_POWER) { if (spB == 1) passB2_body<T, OUT_POWER, 1>(Q, smp, x, y, t, ntB); else if (spB == 4) passB2_body<T, OUT_POWER, 4>(Q, smp, x, y, t, ntB); else if (spB == 8) passB2_body<T, OUT_POWER, 8>(Q, smp, x, y, t, ntB); else if (spB == 9) passB2_body<T, OUT_POWER, 9>(Q, smp, x, y, t, ntB); else if (spB == 10) passB2_body<T, OUT_POWER, 10>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_POWER, 0>(Q, smp, x, y, t, ntB); }
                         else if (output == OUT_ABS) passB2_body<T, OUT_ABS, 0>(Q, smp, x, y, t, ntB);
                         else { if (spB == 1) passB2_body<T, OUT_CWT, 1>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_CWT, 0>(Q, smp, x, y, t, ntB); }
                     });

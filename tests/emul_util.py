@@ -19,7 +19,7 @@ def _build():
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "nwcwt.h")]
     if os.path.isfile(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB, SRC])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DNW_BIG_RADIX=1", "-fPIC", "-shared", "-o", LIB, SRC])
 
 
 _lib = None

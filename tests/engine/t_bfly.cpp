@@ -25,4 +25,4 @@ template <typename T, int R, int DIR> double test() {
     return err;
 }
 #define TST(R) printf("R=%2d  f32 %+d: %.2e %.2e   f64: %.2e %.2e\n", R, 1, test<float, R, 1>(), test<float, R, -1>(), test<double, R, 1>(), test<double, R, -1>());
-int main() { TST(2) TST(3) TST(4) TST(5) TST(6) TST(8) TST(10) TST(12) TST(15) TST(16) TST(20) return 0; }
+int main() { TST(2) TST(3) TST(4) TST(5) TST(6) TST(8) TST(10) TST(12) TST(15) TST(16) TST(20) TST(24) TST(25) TST(30) TST(32) return 0; }
