@@ -46,7 +46,7 @@ WORKLOADS = {
 # cfg5: long-signal sweep, 256 ch x 2^k samples x 256 freqs.  The full output (256 x 256 x N reals) exceeds device memory
 # from 2^20 on, so one step processes as many of the 256 channels as fit a 70 GB output buffer and the buffer is
 # recycled step after step ("streamed"); points/s is per processed point either way.
-for _k in (16, 18, 20, 22, 24, 26):
+for _k in (16, 18, 20, 21, 22, 24, 26):
     _S = max(1, min(256, int(70e9 // (256 * (1 << _k) * 4))))
     WORKLOADS["cfg5_%d" % _k] = dict(
         desc="cfg5: 2^%d samples x 256 freqs, Morse power, %d of 256 ch per step (output buffer recycled)" % (_k, _S),

@@ -60,7 +60,10 @@ template <> struct StaticPlan<8> { static const int P = 1024, R0 = 32, R1 = 32, 
 template <> struct StaticPlan<9> { static const int P = 960, R0 = 32, R1 = 30, R2 = 1, TPS = 2; };
 template <> struct StaticPlan<10> { static const int P = 800, R0 = 32, R1 = 25, R2 = 1, TPS = 2; };
 template <> struct StaticPlan<11> { static const int P = 625, R0 = 25, R1 = 25, R2 = 1, TPS = 2; };
-static const int N_STATIC_PLANS = 11;
+// fp64 tiles hold half as many columns
+template <> struct StaticPlan<12> { static const int P = 1000, R0 = 10, R1 = 10, R2 = 10, TPS = 1; };
+template <> struct StaticPlan<13> { static const int P = 1024, R0 = 16, R1 = 16, R2 = 4, TPS = 1; };
+static const int N_STATIC_PLANS = 13;
 template <int ID> NW_HD bool static_plan_matches(const Fft2Plan& st, int tpsh) {
     typedef StaticPlan<ID> S;
     if (st.P != S::P || tpsh != S::TPS) return false;
@@ -80,6 +83,8 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     if (static_plan_matches<9>(st, tpsh)) return 9;
     if (static_plan_matches<10>(st, tpsh)) return 10;
     if (static_plan_matches<11>(st, tpsh)) return 11;
+    if (static_plan_matches<12>(st, tpsh)) return 12;
+    if (static_plan_matches<13>(st, tpsh)) return 13;
     return 0;
 }
 

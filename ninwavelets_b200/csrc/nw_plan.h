@@ -466,12 +466,19 @@ inline void plan_shape_fast(HostPlan& hp) {
                     const size_t ba = ((size_t)n1 << ta) * 2 * cs, bb = ((size_t)n2 << tb) * 2 * cs + 16;
                     const int ca = ctas(ba), cb = ctas(bb);
                     if (!ca || !cb) continue;
-                    double score = 100.0 * (ta + tb) + 60.0 * (ca + cb) - 40.0 * (a.nst + b.nst);
-                    for (int i = 0; i < a.nst; ++i) if (a.radix[i] >= 15) score -= 25.0;   // register pressure
-                    for (int i = 0; i < b.nst; ++i) if (b.radix[i] >= 15) score -= 25.0;
+                    // lane pairs per tile: the step from one pair to two is worth more than from two to four
+                    // (measured: fp64 2^20, 1024 x 1024 with two pairs each beats 2048 x 512 with one and four)
+                    static const double TPS_SCORE[3] = {0.0, 120.0, 200.0};
+                    // resident CTAs matter more to pass A, the run length of the intermediate more to pass B (measured: 2^24 fp32
+                    // and 2^22 fp64 are fastest with one pair / three CTAs in pass A and two pairs / one CTA in pass B)
+                    double score = TPS_SCORE[ta] + TPS_SCORE[tb] + 80.0 * ca + 55.0 * cb - 40.0 * (a.nst + b.nst);
+                    for (int i = 0; i < a.nst; ++i) if (a.radix[i] >= 15) score -= 15.0;   // register pressure (measured: cfg5 2^18 sweep)
+                    for (int i = 0; i < b.nst; ++i) if (b.radix[i] >= 15) score -= 15.0;
                     if (n1 & 1) score -= 30.0;                 // unaligned output pairs
                     if (n2 >= n1) score += 5.0;
-                    score -= 10.0 * fabs(log2((double)n1 / (double)n2));
+                    // pass A writes the intermediate in runs of (2 << tb) values: below 64 bytes the stores waste sectors
+                    for (size_t run = ((size_t)2 << tb) * cs; run < 64; run *= 2) score -= 20.0;
+                    score -= 4.0 * fabs(log2((double)n1 / (double)n2));
                     if (score > bestScore) {
                         bestScore = score;
                         hp.fast = 1;
@@ -587,7 +594,7 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
             double score = 100.0 * std::min(ta, 8) + 100.0 * std::min(tb, 8);
             if (n1 % tb == 0) score += 50.0;
             if (n2 % ta == 0) score += 25.0;
-            score -= 10.0 * fabs(log2((double)n1 / (double)n2));
+            score -= 4.0 * fabs(log2((double)n1 / (double)n2));
             if (score > bestScore) { bestScore = score; best1 = n1; bestTA = ta; bestTB = tb; }
         }
     }
