@@ -63,7 +63,11 @@ template <> struct StaticPlan<11> { static const int P = 625, R0 = 25, R1 = 25, 
 // fp64 tiles hold half as many columns
 template <> struct StaticPlan<12> { static const int P = 1000, R0 = 10, R1 = 10, R2 = 10, TPS = 1; };
 template <> struct StaticPlan<13> { static const int P = 1024, R0 = 16, R1 = 16, R2 = 4, TPS = 1; };
-static const int N_STATIC_PLANS = 13;
+// long rows (2^22 ... 2^24)
+template <> struct StaticPlan<14> { static const int P = 2048, R0 = 16, R1 = 16, R2 = 8, TPS = 1; };
+template <> struct StaticPlan<15> { static const int P = 4096, R0 = 16, R1 = 16, R2 = 16, TPS = 0; };
+template <> struct StaticPlan<16> { static const int P = 4096, R0 = 16, R1 = 16, R2 = 16, TPS = 1; };
+static const int N_STATIC_PLANS = 16;
 template <int ID> NW_HD bool static_plan_matches(const Fft2Plan& st, int tpsh) {
     typedef StaticPlan<ID> S;
     if (st.P != S::P || tpsh != S::TPS) return false;
@@ -85,6 +89,9 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     if (static_plan_matches<11>(st, tpsh)) return 11;
     if (static_plan_matches<12>(st, tpsh)) return 12;
     if (static_plan_matches<13>(st, tpsh)) return 13;
+    if (static_plan_matches<14>(st, tpsh)) return 14;
+    if (static_plan_matches<15>(st, tpsh)) return 15;
+    if (static_plan_matches<16>(st, tpsh)) return 16;
     return 0;
 }
 

@@ -1,3 +1,4 @@
+# measurement table of a build: every config in fp32 / fp64 (tuning runs: no host leg, no CPU baseline)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 run() {
@@ -7,13 +8,11 @@ import json
 l=[x for x in open('gpurun_out/bench_$tag.log') if x.startswith('{')]
 if not l: print("$tag", 'FAILED', open('gpurun_out/bench_$tag.log').read()[-600:])
 else:
-    d=json.loads(l[-1]); c=d['config']; e=d.get('e2e') or {}
-    print("$tag", ': ms/step %.2f  %.1f Gpts/s  frac %.3f  path %s split %s e2e %s  parity %.1e cpu %s' % (d['ms_per_step'], d['value']/1e9, d['roofline']['frac'], c['path'], c['split'], ('%.1f' % (e['value']/1e9)) if e.get('value') else None, d['parity_spot_check']['max_row_rel_l2'], (d.get('cpu_baseline') or {}).get('sample')))
+    d=json.loads(l[-1]); c=d['config']
+    print("| $tag | %s | %s | %s | %.2f | %.1f | %.3f | %.1e |" % (c['split'], c['radices'], c['threads'], d['ms_per_step'], d['value']/1e9, d['roofline']['frac'], d['parity_spot_check']['max_row_rel_l2']))
 PY
 }
-run cfg2_f64 --workload cfg2 --dtype f64 --steps 5
-run cfg3_f64 --workload cfg3 --dtype f64 --steps 5 --tuning
-run cfg4_f64 --workload cfg4 --dtype f64 --steps 5 --tuning
-for k in 16 18 20 22 24 26; do run cfg5_$k --workload cfg5_$k --steps 3 --tuning; done
-run cfg5_24_f64 --workload cfg5_24 --dtype f64 --steps 3 --tuning
-run cfg2 --steps 20
+for dt in f32 f64; do
+for wl in cfg2 cfg3 cfg4; do run ${wl}_$dt --workload $wl --dtype $dt --steps 5 --tuning; done
+for k in 16 18 20 22 24 26; do run cfg5_${k}_$dt --workload cfg5_$k --dtype $dt --steps 3 --tuning; done
+done
