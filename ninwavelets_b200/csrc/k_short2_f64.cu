@@ -1,3 +1,3 @@
 #define NW_REAL double
-#define NW_S2_MAXREG 128
+#define NW_S2_MAXREG 168
 #include "nw_kern_short2.cuh"

@@ -14,7 +14,7 @@
 namespace nw {
 template <int CFG> struct Cfg2;
 // registers per thread so that (threads x CTAs) of nw_plan.h's CFG2 table stay resident
-template <> struct Cfg2<0> { static const int maxreg = NW_CFG0_MAXREG; };   // 256 x 3 (fp64: 256 x 2)
+template <> struct Cfg2<0> { static const int maxreg = NW_CFG0_MAXREG; };   // 256 x 3 (fp64: 168 registers, 128 x 3)
 template <> struct Cfg2<1> { static const int maxreg = 96; };               // 224 x 3
 template <> struct Cfg2<2> { static const int maxreg = 96; };               // 128 x 5
 template <> struct Cfg2<3> { static const int maxreg = 128; };              //  64 x 8

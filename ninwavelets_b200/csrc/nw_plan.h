@@ -493,9 +493,22 @@ inline void plan_shape_fast(HostPlan& hp) {
     const int ncfg = hp.dtype == 0 ? 4 : 1;   // fp64 kernels exist in shape 0 only; shapes 4, 5 are opt-in
     pick_threads2(hp.stA2, hp.tpshA, hp.smem_A2, ncfg, hp.nthrA2, hp.cfgA);
     pick_threads2(hp.stB2, hp.tpshB, hp.smem_B2, ncfg, hp.nthrB2, hp.cfgB);
-    if (hp.dtype == 0) {   // tuning overrides (fp32 shapes only)
-        hp.nthrA2 = env_int("NWCWT_NTHR_A", hp.nthrA2);
-        hp.nthrB2 = env_int("NWCWT_NTHR_B", hp.nthrB2);
+    if (hp.dtype == 1) {   // fp64 kernels: 168 registers, three 128-thread CTAs per SM (measured: +6 % cfg2, +20 % 2^20 over 256 x 2 at 128)
+        // tiles that leave room for only two or one CTA per SM take 192 / 384 threads (the register file holds 390 x 168)
+        auto cap64 = [](size_t smem, const Fft2Plan& st, int tpsh) {
+            long long maxnb = 0;
+            for (int s = 0; s < st.nst; ++s) maxnb = std::max(maxnb, (long long)(st.P / st.radix[s]) << tpsh);
+            const int fit = (int)((SMEM_MAX + 1024) / (smem + 1024));
+            const int cap = fit >= 3 ? 128 : fit == 2 ? 192 : 384;
+            if (fit == 1) return cap;   // a lone CTA: more warps than butterflies still pays (tile load, epilogue; measured 2^24)
+            return (int)std::min<long long>(cap, (maxnb + 31) / 32 * 32);
+        };
+        hp.nthrA2 = cap64(hp.smem_A2, hp.stA2, hp.tpshA);
+        hp.nthrB2 = cap64(hp.smem_B2, hp.stB2, hp.tpshB);
+    }
+    hp.nthrA2 = env_int("NWCWT_NTHR_A", hp.nthrA2);   // tuning overrides
+    hp.nthrB2 = env_int("NWCWT_NTHR_B", hp.nthrB2);
+    if (hp.dtype == 0) {   // launch shapes exist in fp32 only
         hp.cfgA = env_int("NWCWT_CFG_A", hp.cfgA);
         hp.cfgB = env_int("NWCWT_CFG_B", hp.cfgB);
     }
