@@ -59,6 +59,7 @@ struct HostPlan {
     int cfgA = 0, cfgB = 0;      // compiled launch shape (CFG2_*) of each pass
     int generic_ok = 1;          // long path: the generic two-pass kernels also have a plan for this N
     int narrowA = 0;             // every band touches <= N1 / R_last rows: pass A's first pass needs no loads (nw_kernels2.cuh)
+    std::vector<char> narrow_ok; // the same per frequency: a launch group whose rows all qualify takes the narrow kernel
     int pruneA = 0;              // pass A runs the pruned kernel (per-frequency PrunePlan, FreqRec::pad_)
     std::vector<PrunePlan> pplans;
     size_t smem_A2 = 0, smem_B2 = 0;
@@ -388,14 +389,17 @@ inline void plan_prune(HostPlan& hp) {
     hp.pruneA = 0;
     hp.pplans.clear();
     hp.narrowA = 0;
+    hp.narrow_ok.clear();
     if (hp.fast && hp.F > 0 && hp.stA2.nst >= 2 && !env_int("NWCWT_NO_NARROW", 0)) {
         const int step = hp.N1f / hp.stA2.radix[hp.stA2.nst - 1];
         int worst = 0;
+        hp.narrow_ok.assign((size_t)hp.F, 0);
         for (int i = 0; i < hp.F; ++i) {
             const FreqRec& r = hp.rec[i];
             // rows a tile of 2 << tpshA columns can touch: one more than the band's own row span
             const int C = r.hi > r.lo ? (r.hi - 1) / hp.N2f - r.lo / hp.N2f + 2 : 0;
             worst = std::max(worst, C);
+            hp.narrow_ok[(size_t)i] = C <= step;
         }
         hp.narrowA = worst <= step;
     }
@@ -433,6 +437,16 @@ inline void plan_prune(HostPlan& hp) {
         r.pad_ = idx_of[n1b];
     }
     hp.pruneA = 2 * shorter >= hp.F;
+}
+
+// May the launch group of rows [r0, r0 + g) (row = signal * F + frequency) use the narrow-band first pass of pass A?
+inline bool group_narrow(const HostPlan& hp, long long r0, int g) {
+    if (hp.narrow_ok.empty()) return false;
+    if (hp.narrowA) return true;
+    if (g >= hp.F) return false;
+    for (int i = 0; i < g; ++i)
+        if (!hp.narrow_ok[(size_t)((r0 + i) % hp.F)]) return false;
+    return true;
 }
 
 inline int env_int(const char* name, int dflt) {
@@ -526,6 +540,7 @@ inline void plan_shape_fast(HostPlan& hp) {
     if (const char* e = getenv("NWCWT_RING_MB")) ring_mb = (size_t)std::max(1, atoi(e));
     long long ring = (long long)((ring_mb << 20) / slot);
     hp.ring2 = (int)std::max<long long>(1, std::min<long long>(ring, 256));
+    if (env_int("NWCWT_RING_ROWS", 0) > 0) hp.ring2 = std::min(hp.ring2, env_int("NWCWT_RING_ROWS", 0));   // tests: small launch groups
 }
 
 // Packed-engine short kernel: N 2-3-5 smooth, N (1 + NF) two-lane complex values of shared memory with NF = 1, 2, 4

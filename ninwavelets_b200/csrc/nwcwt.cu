@@ -528,7 +528,7 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
                 Q.Tm = Tm + (size_t)slot * (size_t)hp.ring2 * (size_t)hp.tm_stride2;
                 Q.n_sm = device_sms(hp.device);
                 Q.tm_mod = g_tm_mod;
-                Q.narrow = hp.narrowA;
+                Q.narrow = group_narrow(hp, r0, g) ? 1 : 0;
                 if (hp.stA2.nst >= 1) Q.dstepA = make_fastdiv((uint32_t)std::max(1, hp.N1f / hp.stA2.radix[hp.stA2.nst - 1]));
                 Q.skew = g_skew_a; Q.skew_mod = g_skew_mod_a;
                 { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, spA, Q, dim3(tA, g), hp.nthrA2, hp.smem_A2, st)); }

@@ -206,7 +206,7 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
                 for (int y = 0; y < g; ++y) for (int x = 0; x < tA; ++x)
                     Fibers::get().run(ntA, [&](int t) {
                         if (spA == -1) passA2p_body<T>(Q, smp, x, y, t, ntA);
-                        else if (hp.narrowA && !(g_mode & 64)) {
+                        else if (group_narrow(hp, r0, g) && !(g_mode & 64)) {
                             if (spA == 2) passA2_body<T, 2, true>(Q, smp, x, y, t, ntA);
                             else passA2_body<T, 0, true>(Q, smp, x, y, t, ntA);
                         } else {

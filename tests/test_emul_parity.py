@@ -88,6 +88,25 @@ def test_emul_long_path_variants_agree(flags):
         assert l2_rel_err(p.reshape(-1, n), ref32.reshape(-1, n)).max() <= F32_TOL, (kind, flags)
 
 
+@pytest.mark.parametrize("ring_rows", [1, 2, 3])
+def test_emul_narrow_pass_per_launch_group(ring_rows, monkeypatch):
+    """Bands of mixed width: the planner allows the narrow-band first pass of pass A only for launch groups whose
+    frequencies all qualify (nw_plan.h: group_narrow); small groups make both kernels run in one transform."""
+    monkeypatch.setenv("NWCWT_RING_ROWS", str(ring_rows))
+    rng = np.random.default_rng(23)
+    fam = orc.Family("morse", sfreq=1000.0)
+    for n, freqs in ((6000, np.array([1., 2.5, 9., 30., 77., 210., 499.])), (16384, np.array([2., 11., 60., 200., 450.]))):
+        x = rng.standard_normal((2, n))
+        ref = np.stack([orc.cwt(fam, xi, freqs) for xi in x])
+        d = desc_from_oracle_family(fam, freqs, n, dtype=1)
+        z = emul_transform(d, x, output=0, force_long=1 | 16)
+        assert peak_rel_err(z.reshape(-1, n), ref.reshape(-1, n)).max() <= F64_TOL
+        x32 = x.astype(np.float32)
+        ref32 = np.stack([orc.power(fam, xi.astype(np.float64), freqs) for xi in x32])
+        p = emul_transform(desc_from_oracle_family(fam, freqs, n, dtype=0), x32, output=2, force_long=1 | 16)
+        assert l2_rel_err(p.reshape(-1, n), ref32.reshape(-1, n)).max() <= F32_TOL
+
+
 def test_emul_long_65536(golden_transforms):
     c = golden_transforms["morse_long_n65536"]
     fam = orc.Family(c["kind"], **c["kw"])

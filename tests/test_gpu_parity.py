@@ -274,6 +274,25 @@ def test_long_signal_sweep_vs_oracle(nw, e):
         assert peak_rel_err(z, orc.cwt(fam, x, fr)).max() <= F64_TOL, e
 
 
+@pytest.mark.parametrize("ring_rows", [1, 3])
+def test_mixed_band_widths_narrow_and_general_pass_a(nw, ring_rows, monkeypatch):
+    """Frequencies whose bands are narrow enough for the no-load first pass of pass A next to ones that are not:
+    launch groups of 1 or 3 rows make the library pick the kernel group by group (nw_plan.h: group_narrow)."""
+    monkeypatch.setenv("NWCWT_RING_ROWS", str(ring_rows))
+    n = 1 << 18
+    rng = np.random.default_rng(29)
+    x = rng.standard_normal((2, n))
+    fr = np.array([1.0, 4.0, 20.0, 90.0, 180.0, 300.0, 450.0])
+    fam = orc.Family("morse", sfreq=1000)
+    x32 = x.astype(np.float32)
+    p = make(nw, "morse", dict(sfreq=1000), dtype="float32").power(x32, fr)
+    for i in range(2):
+        assert l2_rel_err(p[i].astype(np.float64), orc.power(fam, x32[i].astype(np.float64), fr)).max() <= F32_TOL
+    z = make(nw, "morse", dict(sfreq=1000), dtype="float64").cwt(x, fr)
+    for i in range(2):
+        assert peak_rel_err(z[i], orc.cwt(fam, x[i], fr)).max() <= F64_TOL
+
+
 def test_2_26_properties(nw):
     """N = 2^26 (config 5's largest row; only the packed kernels have a plan): Parseval and linearity in fp32."""
     import torch
