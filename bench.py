@@ -40,6 +40,9 @@ WORKLOADS = {
                  kind="morse", S=64, N=600000, freqs=np.arange(1, 101.0), baseline=None),
     "cfg3": dict(desc="cfg3: 306 ch x 200 epochs x 1500 samples @1 kHz, Morlet(7) power + zscore[0,0.2s], freqs 1-100",
                  kind="morlet", S=306 * 200, N=1500, freqs=np.arange(1, 101.0), baseline=("zscore", 0.0, 0.2)),
+    # cfg3, epoch-mean variant (mneutils.py:53-55): per-epoch power, then the mean over the 200 epochs of each channel
+    "cfg3_mean": dict(desc="cfg3 epoch-mean: 306 ch x 200 epochs x 1500 samples @1 kHz, Morlet(7) power, mean over epochs, freqs 1-100",
+                      kind="morlet", S=306 * 200, N=1500, freqs=np.arange(1, 101.0), baseline=None, epochs=200),
     "cfg4": dict(desc="cfg4: 32 ch x 2^20 samples, Morse power, freqs 1-128",
                  kind="morse", S=32, N=1 << 20, freqs=np.arange(1, 129.0), baseline=None),
 }
@@ -238,8 +241,13 @@ def run_graft(args, wl):
         bl = (be.BASELINE_MODES[wl["baseline"][0]], lo, hi)
     out = torch.empty((S, F, N), dtype=tdt, device=dev)
 
+    n_ep = wl.get("epochs", 0)
+
     def step():
         plan.transform_device(x, be.OUT_POWER, *bl, out=out)
+        if n_ep:   # signals are channel-major: out[c * E + e]
+            ov = out.view(S // n_ep, n_ep, F, N)
+            return [plan.reduce_epochs_device(ov[c], 0) for c in range(S // n_ep)]
 
     def barrier():
         if world > 1:
@@ -357,6 +365,10 @@ def run_graft(args, wl):
         num = np.sqrt(((got - ref) ** 2).sum(axis=1))
         den = np.sqrt((ref ** 2).sum(axis=1))
         parity = {"rows_checked": len(idx), "max_row_rel_l2": float((num / np.maximum(den, 1e-2 * den.max())).max())}
+        if n_ep:   # the epoch mean of channel 0 against a float64 mean of the same per-epoch rows
+            m = step()[0].double()
+            mref = out.view(S // n_ep, n_ep, F, N)[0].double().mean(dim=0)
+            parity["epoch_mean_max_rel"] = float(((m - mref).abs().max() / mref.abs().max()).item())
         # bounded CPU sample of the same workload on this box's host cores (single process = as shipped)
         per, fr = sample_shape(wl)
         reps, dt_sum, pts_sum = 0, 0.0, 0.0

@@ -364,6 +364,8 @@ inline void pick_threads2(const Fft2Plan& st, int tpsh, size_t smem, int ncfg, i
     const int maxthr = CFG2_MAXTHR[cfg];
     if (cfg == 0) {   // fill the shape: more warps beat a better fit of butterflies to threads here
         nthr = (int)std::min<long long>(maxthr, (maxnb + 31) / 32 * 32);
+        // a lone CTA per SM with at least two butterflies per thread left: 512 threads (measured 2^26: 349 -> 324 ms)
+        if (by_smem == 1 && maxnb >= 1024) nthr = 512;
         return;
     }
     const int lo = std::max(32, (int)std::min<long long>(maxthr * 3 / 4, (maxnb + 31) / 32 * 32) / 32 * 32);

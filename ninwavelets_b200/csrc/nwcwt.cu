@@ -797,6 +797,7 @@ int nwcwt_reduce_epochs(nwcwt_plan* pl, const void* in, void* out, int64_t E, in
     if (E <= 0 || count <= 0 || kind < 0 || kind > 1) return fail(NWCWT_ERR_INVALID, "bad reduction arguments");
     CUDA_TRY(cudaSetDevice(pl->hp.device));
     const unsigned grid = (unsigned)((count + 255) / 256);
+    LaunchScope ls(5, (cudaStream_t)stream);
     if (pl->hp.dtype == NWCWT_F32)
         nwcwt_reduce_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(in, (float*)out, E, count, kind);
     else
@@ -815,6 +816,7 @@ int nwcwt_baseline_rows(int32_t device, int32_t dtype, void* rows, int64_t n_row
     if (bhi > n) bhi = n;
     if (blo > bhi) blo = bhi;
     CUDA_TRY(cudaSetDevice(device));
+    LaunchScope ls(5, (cudaStream_t)stream);
     if (dtype == NWCWT_F32)
         nwcwt_baseline_rows_kernel<float><<<(unsigned)n_rows, 512, 0, (cudaStream_t)stream>>>((float*)rows, n, bl, (int)blo, (int)bhi);
     else
