@@ -473,8 +473,8 @@ inline void plan_shape_fast(HostPlan& hp) {
             if (env_int("NWCWT_SPLIT_N1", 0) > 0 && n1 != env_int("NWCWT_SPLIT_N1", 0)) continue;   // tuning override
             Fft2Plan a, b;
             if (!plan_packed(n1, a) || !plan_packed(n2, b)) continue;
-            if (env_int("NWCWT_BIG", 0) & 2) plan_big(n1, a);
-            if (env_int("NWCWT_BIG", 0) & 1) plan_big(n2, b);
+            if (hp.dtype == 0 && (env_int("NWCWT_BIG", 0) & 2)) plan_big(n1, a);   // fp32 kernels only
+            if (hp.dtype == 0 && (env_int("NWCWT_BIG", 0) & 1)) plan_big(n2, b);
             const int fa = env_int("NWCWT_TPSH_A", -1), fb = env_int("NWCWT_TPSH_B", -1);   // tuning overrides
             for (int ta = 2; ta >= 0; --ta)
                 for (int tb = 2; tb >= 0; --tb) {
