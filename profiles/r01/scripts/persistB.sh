@@ -1,3 +1,4 @@
+# historical: the persistent pass-B kernel / NW_TIMING hooks this script measured were removed again (see shape_sweep.md)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/gputests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/gputests.log
