@@ -66,7 +66,10 @@ typedef struct nwcwt_plan_desc {
     int32_t interpolate;  /* WaveletBase.interpolate (base.py:239-242, 276, 400-401) */
     int64_t n;            /* samples per signal, wave.shape[0] */
     int32_t n_freqs;      /* len(freqs) */
-    int32_t reserved;
+    /* Resampled rows (long signals, abs / power output): a row whose non-pruned band holds B << n bins is
+     * computed as an inverse transform of length n / D >= B and interpolated back to n samples.
+     * 0: library default (on), 1: on, -1: off - every row takes the exact length-n inverse transform. */
+    int32_t resample;
     double sfreq;         /* WaveletBase.sfreq */
     const double* freqs;  /* host, [n_freqs] */
     /* Morse (wavelets.py:38-45): p0 = b, p1 = r.
@@ -86,6 +89,10 @@ typedef struct nwcwt_plan_desc {
      * (1e-12 for F32, 1e-24 for F64: far below the rounding noise of the
      * arithmetic itself); 0: evaluate every bin like the reference. */
     double prune_eps;
+    /* Bound on the relative error the interpolation of a resampled row may add, for ANY input (worst case over
+     * single sinusoids in the band).  <= 0: library default, 5e-7 (F32) / 5e-14 (F64) - a quarter of the
+     * arithmetic's own rounding error budget.  The planner reports what it achieved in nwcwt_plan_info. */
+    double resample_tol;
 } nwcwt_plan_desc;
 
 typedef struct nwcwt_plan nwcwt_plan;
@@ -104,7 +111,12 @@ typedef struct nwcwt_plan_info {
     int64_t smem_bytes;    /* dynamic shared memory of the dominant kernel */
     int32_t threads[2];    /* threads per CTA: short kernel / pass A, pass B */
     int32_t rows_per_launch; /* long rows: (signal, frequency) rows per pass-A / pass-B launch pair */
-    int32_t reserved;
+    int32_t n_groups;      /* resampled rows: groups of frequencies by decimation (0: every row exact) */
+    int32_t group_D[32];   /* decimation of each group (1 = exact rows) */
+    int32_t group_K[32];   /* interpolation taps */
+    int32_t group_rows[32];/* frequencies in the group */
+    int32_t group_n1[32], group_n2[32]; /* split of the group's transform length n / D */
+    double group_err[32];  /* worst-case relative interpolation error of the group (any input) */
 } nwcwt_plan_info;
 
 int nwcwt_version(void);
@@ -114,12 +126,15 @@ int64_t nwcwt_launch_count(void);
 /* Kernel-class timing for bench.py's roofline: when enabled, every launch of the transform's kernels is
  * bracketed by CUDA events on the launching stream; nwcwt_profile_read synchronises and returns the
  * accumulated milliseconds and launch counts of [0] short fused kernel, [1] forward pass A, [2] forward
- * pass B, [3] inverse pass A, [4] inverse pass B, [5] baseline rows, and resets them. */
+ * pass B, [3] inverse pass A, [4] inverse pass B, [5] baseline rows / epoch reductions, [6] interpolation of
+ * resampled rows, [7] reserved, and resets them. */
 int nwcwt_profile_enable(int32_t on);
 /* Test hook: non-zero makes every transform use the generic (any-length) kernels even where the plan has
  * the packed fast path, so both can be checked against the oracle on the same input. */
 int nwcwt_debug_force_generic(int32_t on);
-int nwcwt_profile_read(double ms[6], int64_t launches[6]);
+int nwcwt_profile_read(double ms[8], int64_t launches[8]);
+/* Test hook: non-zero makes a plan with resampled rows run the exact length-n transform for every row. */
+int nwcwt_debug_force_exact(int32_t on);
 
 /* Host-side planning only (no CUDA call): factorisation, bands, tables.  Device
  * resources are created on first use.  Replaces make_fft_wavelets, base.py:258-279. */

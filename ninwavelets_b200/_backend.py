@@ -26,12 +26,12 @@ ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_ZERO_FREQ = -1, -2, -
 class PlanDesc(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("dtype", C.c_int32), ("family", C.c_int32), ("interpolate", C.c_int32),
-        ("n", C.c_int64), ("n_freqs", C.c_int32), ("reserved", C.c_int32),
+        ("n", C.c_int64), ("n_freqs", C.c_int32), ("resample", C.c_int32),
         ("sfreq", C.c_double), ("freqs", C.POINTER(C.c_double)),
         ("p0", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
         ("aux", C.POINTER(C.c_double)),
         ("table", C.POINTER(C.c_double)), ("table_len", C.c_int64), ("table_lens", C.POINTER(C.c_int64)),
-        ("prune_eps", C.c_double),
+        ("prune_eps", C.c_double), ("resample_tol", C.c_double),
     ]
 
 
@@ -40,7 +40,9 @@ class PlanInfo(C.Structure):
         ("n", C.c_int64), ("n_freqs", C.c_int32), ("path", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32),
         ("batch", C.c_int32), ("n_stages", C.c_int32 * 2), ("radices", (C.c_int32 * 16) * 2),
         ("band_bins", C.c_int64), ("smem_bytes", C.c_int64),
-        ("threads", C.c_int32 * 2), ("rows_per_launch", C.c_int32), ("reserved", C.c_int32),
+        ("threads", C.c_int32 * 2), ("rows_per_launch", C.c_int32), ("n_groups", C.c_int32),
+        ("group_D", C.c_int32 * 32), ("group_K", C.c_int32 * 32), ("group_rows", C.c_int32 * 32),
+        ("group_n1", C.c_int32 * 32), ("group_n2", C.c_int32 * 32), ("group_err", C.c_double * 32),
     ]
 
 
@@ -59,6 +61,7 @@ SYMBOLS = (
     "nwcwt_plan_get_bands", "nwcwt_workspace_bytes", "nwcwt_spectrum_bank", "nwcwt_reduce_epochs",
     "nwcwt_baseline_rows", "nwcwt_launch_count", "nwcwt_profile_enable", "nwcwt_profile_read",
     "nwcwt_forward", "nwcwt_transform", "nwcwt_transform_host", "nwcwt_debug_force_generic",
+    "nwcwt_debug_force_exact",
 )
 
 
@@ -107,7 +110,13 @@ def launch_count():
     return int(lib().nwcwt_launch_count())
 
 
-PROFILE_CLASSES = ("short_fused", "fwd_passA", "fwd_passB", "inv_passA", "inv_passB", "baseline_rows")
+PROFILE_CLASSES = ("short_fused", "fwd_passA", "fwd_passB", "inv_passA", "inv_passB", "baseline_rows", "resample",
+                   "reserved")
+
+
+def force_exact(on):
+    """Test hook: plans with resampled rows run the exact length-n transform for every row."""
+    _check(lib().nwcwt_debug_force_exact(C.c_int32(1 if on else 0)))
 
 
 def force_generic(on):
@@ -120,8 +129,8 @@ def profile_enable(on):
 
 
 def profile_read():
-    ms = (C.c_double * 6)()
-    n = (C.c_int64 * 6)()
+    ms = (C.c_double * 8)()
+    n = (C.c_int64 * 8)()
     _check(lib().nwcwt_profile_read(ms, n))
     return {k: dict(ms=ms[i], launches=int(n[i])) for i, k in enumerate(PROFILE_CLASSES)}
 
@@ -134,7 +143,7 @@ class Plan:
     """Device-side counterpart of `WaveletBase.fft_wavelets` for one (family, freqs, N, dtype)."""
 
     def __init__(self, *, device, dtype, family, interpolate, n, sfreq, freqs, p0=0.0, p1=0.0, p2=0.0,
-                 aux=None, table=None, table_lens=None, prune_eps=-1.0):
+                 aux=None, table=None, table_lens=None, prune_eps=-1.0, resample=None, resample_tol=0.0):
         self._h = C.c_void_p()
         self.dtype = F64 if np.dtype(dtype) == np.float64 else F32
         self.real_dtype = np.dtype(np.float64 if self.dtype == F64 else np.float32)
@@ -164,6 +173,8 @@ class Plan:
                 d.table_lens = table_lens.ctypes.data_as(C.POINTER(C.c_int64))
                 keep.append(table_lens)
         d.prune_eps = -1.0 if prune_eps is None else float(prune_eps)
+        d.resample = 0 if resample is None else (1 if resample else -1)
+        d.resample_tol = float(resample_tol or 0.0)
         _check(lib().nwcwt_plan_create(C.byref(self._h), C.byref(d)))
         del keep
         self._ws = None
@@ -176,6 +187,8 @@ class Plan:
                    batch=i.batch, band_bins=i.band_bins, smem_bytes=i.smem_bytes, threads=list(i.threads),
                    rows_per_launch=i.rows_per_launch)
         out["radices"] = [list(i.radices[k][: i.n_stages[k]]) for k in range(2)]
+        out["groups"] = [dict(D=i.group_D[g], K=i.group_K[g], rows=i.group_rows[g], n1=i.group_n1[g], n2=i.group_n2[g],
+                              err=i.group_err[g]) for g in range(i.n_groups)]
         return out
 
     def bands(self):

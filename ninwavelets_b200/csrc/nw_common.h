@@ -117,15 +117,4 @@ struct Fft2Plan {
     fastdiv div_r[MAX_STAGES2];   // x / radix[s]
 };
 
-// Pruned column transform of the fast long path: a frequency whose non-zero band touches C <= n1b of the N1
-// rows needs only n1a = N1 / n1b phase-shifted transforms of length n1b per column ("input pruning").
-struct PrunePlan {
-    Fft2Plan st;      // plan of length n1b
-    int n1a, nseq;    // phases per column; interleaved sequences per tile = (columns / 2) * n1a
-    fastdiv dseq;     // x / nseq
-    fastdiv dn1a;     // x / n1a
-    fastdiv dn1b;     // x / n1b
-    fastdiv dn1a1;    // x / (n1a - 1)   (n1a > 1)
-};
-
 }  // namespace nw

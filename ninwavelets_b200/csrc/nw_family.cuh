@@ -22,9 +22,10 @@ namespace nw {
 // Per-frequency record prepared by the host planner (all doubles evaluated with
 // the same operation order as the reference).
 struct FreqRec {
-    int lo, hi;     // band of non-zero bins on the N-bin axis
-    int toff;       // TABLE: bin of table element 0 (pad_to front offset of this row)
-    int pad_;
+    int lo, hi;     // band of non-zero bins, in (signed) transform bins: data bin = transform bin + shift
+    int toff;       // TABLE: data bin of table element 0 (pad_to front offset of this row)
+    int shift;      // 0 except in the plan of a resampled group (nw_resample.cuh), whose M-point spectrum holds the
+                    // band around bin 0 (negative bins wrap to the top end)
     double freq;    // analysis frequency (Hz)
     double aux;     // Morlet: peak_freq(freq)
     double kx;      // fp32 path: x = (k - grid_off) * kx   (df/freq [* peak])

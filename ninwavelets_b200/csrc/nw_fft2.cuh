@@ -126,29 +126,15 @@ NW_HD void dif_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
         if (LAST) ctx = dst.begin(g.rev(blk), g.P / R, tp);   // issues the epilogue's own loads early
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = RAW ? raw_to_packed<T>(e[r * stride]) : e[r * stride];
-#if !defined(NW_KNOCKOUT) || NW_KNOCKOUT != 1
         B2<T, R, DIR>::run(v);
-#endif
         if (LAST) {
             dst.template store_all<R>(ctx, v);
         } else {
-#if defined(NW_KNOCKOUT) && NW_KNOCKOUT == 1      /* timing experiment: no arithmetic */
-#pragma unroll
-            for (int r = 0; r < R; ++r) e[r * stride] = v[r];
-#elif defined(NW_KNOCKOUT) && NW_KNOCKOUT == 2    /* timing experiment: no shared-memory stores */
-            cx<T> w[R];
-            tw_powers<T, R>(tw_dir<T, DIR>(tw[np * g.tws]), w);
-            cx2<T> acc = v[0];
-#pragma unroll
-            for (int r = 1; r < R; ++r) acc = acc + cmul_s(v[r], w[r]);
-            if (pk_lo(acc.re) == (T)123.456) e[0] = acc;
-#else
             cx<T> w[R];
             tw_powers_tab<T, R, DIR>(tw, np * g.tws, w);
             e[0] = v[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) e[r * stride] = cmul_s(v[r], w[r]);
-#endif
         }
     }
 }
@@ -173,11 +159,6 @@ NW_HD void dif_stage_any(const Fft2Plan& st, int s, const SeqDesc& tpsh, const c
         case 12: dif_stage<T, 12, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
         case 15: dif_stage<T, 15, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
         case 16: dif_stage<T, 16, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
-#ifdef NW_BIG_RADIX
-        case 25: dif_stage<T, 25, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
-        case 30: dif_stage<T, 30, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
-        case 32: dif_stage<T, 32, DIR, LAST, RAW>(st, s, tpsh, tw, buf, dst, tid, nthr); break;
-#endif
         default: break;
     }
 }
@@ -269,9 +250,7 @@ NW_HD void dit_body(const G& g, const cx<T>* NW_RESTRICT tw, cx2<T>* buf, const 
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = cmul_s(e[r * stride], w[r]);
         }
-#if !defined(NW_KNOCKOUT) || NW_KNOCKOUT != 5   /* 5: timing experiment, no butterflies in the DIT passes */
         B2<T, R, DIR>::run(v);
-#endif
         if (LAST) {
             dst.template store_all<R>(ctx, v);
         } else {
@@ -301,11 +280,6 @@ NW_HD void dit_stage_any(const Fft2Plan& st, int s, const SeqDesc& tpsh, const c
         case 12: dit_stage<T, 12, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
         case 15: dit_stage<T, 15, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
         case 16: dit_stage<T, 16, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
-#ifdef NW_BIG_RADIX
-        case 25: dit_stage<T, 25, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
-        case 30: dit_stage<T, 30, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
-        case 32: dit_stage<T, 32, DIR, FIRST, LAST>(st, s, tpsh, tw, buf, src, dst, tid, nthr); break;
-#endif
         default: break;
     }
 }

@@ -18,8 +18,6 @@ template <> struct Cfg2<0> { static const int maxreg = NW_CFG0_MAXREG; };   // 2
 template <> struct Cfg2<1> { static const int maxreg = 96; };               // 224 x 3
 template <> struct Cfg2<2> { static const int maxreg = 96; };               // 128 x 5
 template <> struct Cfg2<3> { static const int maxreg = 128; };              //  64 x 8
-template <> struct Cfg2<4> { static const int maxreg = 255; };              // 128 x 2  (radix 25-32 plans)
-template <> struct Cfg2<5> { static const int maxreg = 168; };              // 128 x 3
 
 template <typename T, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2_kernel(const __grid_constant__ Long2Params<T> P) {
@@ -30,11 +28,6 @@ template <typename T, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2n_kernel(const __grid_constant__ Long2Params<T> P) {
     extern __shared__ __align__(32) char nw_smem[];
     passA2_body<T, SP, true>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
-}
-template <typename T, int CFG>
-__global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2p_kernel(const __grid_constant__ Long2Params<T> P) {
-    extern __shared__ __align__(32) char nw_smem[];
-    passA2p_body<T>(P, nw_smem, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
 template <typename T, int CFG>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2f_kernel(const __grid_constant__ Long2Params<T> P) {
@@ -86,7 +79,6 @@ template <typename T, int CFG, int SP> static cudaError_t runB(const Long2Params
 template <> cudaError_t prepare_long2<NW_REAL, NW_CFG>() {
     { cudaError_t e = cudaFuncSetAttribute(nwcwt_passA2f_kernel<NW_REAL, NW_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
     { cudaError_t e = cudaFuncSetAttribute(nwcwt_passB2f_kernel<NW_REAL, NW_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
-    { cudaError_t e = cudaFuncSetAttribute(nwcwt_passA2p_kernel<NW_REAL, NW_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
     NW_PREP_A(0) NW_SP_A(NW_PREP_A)
     NW_PREP_B(0) NW_SP_B(NW_PREP_B)
     return cudaSuccess;
@@ -100,10 +92,6 @@ template <>
 cudaError_t launch_passA2<NW_REAL, NW_CFG>(int sp, const Long2Params<NW_REAL>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s) {
     if (sp == -2) {   // forward transform
         nwcwt_passA2f_kernel<NW_REAL, NW_CFG><<<grid, nthr, smem, s>>>(P);
-        return cudaGetLastError();
-    }
-    if (sp < 0) {   // pruned column transforms (per-frequency plans)
-        nwcwt_passA2p_kernel<NW_REAL, NW_CFG><<<grid, nthr, smem, s>>>(P);
         return cudaGetLastError();
     }
     switch (sp) {

@@ -20,7 +20,8 @@ namespace nw {
 
 template <typename T>
 struct Long2Params {
-    long long N;
+    long long N;        // transform length N1 * N2 (a resampled group's plan: the decimated length M)
+    long long xstride;  // elements between the spectra of consecutive signals in X (the data length Nd)
     int N1, N2, F;
     int tpshA;          // pass A: 2 << tpshA columns per CTA
     int tpshB;          // pass B: 2 << tpshB rows (n1) per CTA
@@ -31,16 +32,19 @@ struct Long2Params {
     const cx<T>* twL;   // w_N^{j}, j < 1 << lb
     int lb;
     const T* signal;    // forward transform: real signals of this launch, [nsig][N]
-    const cx<T>* X;     // spectra of the signals of this group, [nsig][N]
+    const cx<T>* X;     // spectra of the signals of this group, [nsig][xstride]
     cx<T>* Tm;          // intermediate ring, [rows][tm_stride]
     long long tm_stride;
     void* out;          // output of row 0 of the group
-    const PrunePlan* pplans;   // pruned pass A: plans indexed by FreqRec::pad_
-    int skew, skew_mod; // start-up stagger of the first wave: CTA waits ((linear block id / n_sm) % skew_mod) * skew cycles
-    int n_sm;
+    // frequency subsets (resampled groups, nw_resample.cuh): launch row (signal si, local frequency fi) writes output
+    // row si * F_out + fmap[fi]; fmap == nullptr: row si * F + fi
+    const int* fmap;
+    int F_out;
+    // resampled groups: eq[|j|] = D / H(j), the inverse of the interpolation kernel's frequency response at the
+    // (signed) transform bin j - applied to the spectrum so that the interpolated row is exact in the pass band
+    const T* eq;
     int narrow;         // launch the narrow-band variant of pass A (host side only)
     fastdiv dstepA;     // narrow-band pass A: x / (N1 / radix of the first pass)
-    int tm_mod;         // timing experiment only: rows share Tm slots (by % tm_mod); 0 = off
     int row0;           // first row (signal-major: row = signal * F + frequency) of this launch
     int out_mode;
     SpecParams<T> sp;
@@ -55,11 +59,6 @@ template <> struct StaticPlan<4> { static const int P = 256, R0 = 16, R1 = 16, R
 template <> struct StaticPlan<5> { static const int P = 512, R0 = 16, R1 = 8, R2 = 4, TPS = 2; };
 template <> struct StaticPlan<6> { static const int P = 1500, R0 = 10, R1 = 10, R2 = 15, TPS = 1; };   // short rows, cfg3
 template <> struct StaticPlan<7> { static const int P = 300, R0 = 12, R1 = 5, R2 = 5, TPS = 3; };      // short rows, cfg1
-// two-pass plans with radix 25-32 butterflies (launch shapes 4 and 5, NW_BIG_RADIX translation units)
-template <> struct StaticPlan<8> { static const int P = 1024, R0 = 32, R1 = 32, R2 = 1, TPS = 2; };
-template <> struct StaticPlan<9> { static const int P = 960, R0 = 32, R1 = 30, R2 = 1, TPS = 2; };
-template <> struct StaticPlan<10> { static const int P = 800, R0 = 32, R1 = 25, R2 = 1, TPS = 2; };
-template <> struct StaticPlan<11> { static const int P = 625, R0 = 25, R1 = 25, R2 = 1, TPS = 2; };
 // fp64 tiles hold half as many columns
 template <> struct StaticPlan<12> { static const int P = 1000, R0 = 10, R1 = 10, R2 = 10, TPS = 1; };
 template <> struct StaticPlan<13> { static const int P = 1024, R0 = 16, R1 = 16, R2 = 4, TPS = 1; };
@@ -83,34 +82,12 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     if (static_plan_matches<5>(st, tpsh)) return 5;
     if (static_plan_matches<6>(st, tpsh)) return 6;
     if (static_plan_matches<7>(st, tpsh)) return 7;
-    if (static_plan_matches<8>(st, tpsh)) return 8;
-    if (static_plan_matches<9>(st, tpsh)) return 9;
-    if (static_plan_matches<10>(st, tpsh)) return 10;
-    if (static_plan_matches<11>(st, tpsh)) return 11;
     if (static_plan_matches<12>(st, tpsh)) return 12;
     if (static_plan_matches<13>(st, tpsh)) return 13;
     if (static_plan_matches<14>(st, tpsh)) return 14;
     if (static_plan_matches<15>(st, tpsh)) return 15;
     if (static_plan_matches<16>(st, tpsh)) return 16;
     return 0;
-}
-
-// CTAs of one launch start together and, doing identical work, would run their load / butterfly / store phases in
-// lockstep, leaving the FP32 pipe idle while all of them load and the LSU idle while all of them compute.  A one-time
-// stagger of the first wave (later CTAs inherit it from the slot they take over) de-phases the CTAs of an SM.
-template <typename T> NW_HD void first_wave_stagger(const Long2Params<T>& P, int bx, int by, int gx) {
-#if defined(__CUDA_ARCH__)
-    if (P.skew > 0) {
-        const unsigned lin = (unsigned)by * (unsigned)gx + (unsigned)bx;
-        if (lin < (unsigned)(P.n_sm * P.skew_mod)) {
-            const long long wait = (long long)((lin / (unsigned)P.n_sm) % (unsigned)P.skew_mod) * P.skew;
-            const long long t0 = clock64();
-            while (clock64() - t0 < wait) {}
-        }
-    }
-#else
-    (void)P; (void)bx; (void)by; (void)gx;
-#endif
 }
 
 template <typename T, int DIR = 1> NW_HD cx<T> big_twiddle2(const Long2Params<T>& P, int m) {
@@ -127,34 +104,24 @@ template <typename T, int DIR = 1> struct TmDst2 {
     const Long2Params<T>* P;
     cx<T>* tm;
     int c;
-    int n1a;          // pruned transform: sequence t = tp * n1a + a computes rows n1 = a + n1a * b; else 1
-    fastdiv dn1a;
     struct Ctx {
         cx2<T> cur, g;
         cx<T>* col;
         uint32_t n1, step;
         bool valid, two;
     };
-    NW_HD Ctx begin(int base, int step, int t) const {
+    NW_HD Ctx begin(int base, int step, int tp) const {
         Ctx x;
         const int N2 = P->N2;
-        int tp = t, a = 0;
-        if (n1a > 1) { tp = (int)fd_div((uint32_t)t, dn1a); a = t - tp * n1a; }
         const int k2 = c + 2 * tp;
         x.valid = k2 < N2;
         x.two = k2 + 1 < N2;
         const int k2a = x.valid ? k2 : 0, k2b = x.two ? k2 + 1 : k2a;
-        const int n1 = a + n1a * base, dn1 = n1a * step;
-#if defined(NW_KNOCKOUT) && NW_KNOCKOUT == 4   /* timing experiment: no twiddle-table look-ups */
-        x.cur = mk2<T>(mk<T>((T)1, (T)(k2a * n1)), mk<T>((T)1, (T)0));
-        x.g = mk2<T>(mk<T>((T)1, (T)dn1), mk<T>((T)1, (T)0));
-#else
-        x.cur = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * n1), big_twiddle2<T, DIR>(*P, k2b * n1));
-        x.g = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * dn1), big_twiddle2<T, DIR>(*P, k2b * dn1));
-#endif
+        x.cur = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * base), big_twiddle2<T, DIR>(*P, k2b * base));
+        x.g = mk2<T>(big_twiddle2<T, DIR>(*P, k2a * step), big_twiddle2<T, DIR>(*P, k2b * step));
         x.col = tm + ((size_t)k2a << (P->tpshB + 1));
-        x.n1 = (uint32_t)n1;
-        x.step = (uint32_t)dn1;
+        x.n1 = (uint32_t)base;
+        x.step = (uint32_t)step;
         return x;
     }
     template <int R> NW_HD void store_all(const Ctx& x, const cx2<T>* v) const {
@@ -170,32 +137,39 @@ template <typename T, int DIR = 1> struct TmDst2 {
         for (int q = 0; q < R; ++q, n1 += x.step) {
             const cx2<T> y = cmul_p(v[q], cur[q & 1]);
             if (q + 2 < R) cur[q & 1] = cmul_p(cur[q & 1], g2);
-            // Tm holds plain complex values, TB consecutive rows n1 of one column contiguous.  (-DNW_TM_PACKED: lane-packed
-            // units {re(n1), re(n1+1), im(n1), im(n1+1)} written as four scalars - no repacking in pass B but twice the
-            // store sectors; measured 2.6 % slower per cfg2 step.)
+            // Tm holds plain complex values, TB consecutive rows n1 of one column contiguous: 8-byte stores that fill
+            // whole sectors; pass B repacks pairs of rows into lanes in its first pass
             const size_t e = (size_t)((n1 >> shB) * blk + (n1 & mask));          // complex index within the column pair's rows
-            T* o = (T*)x.col + (((e >> 1) << 2) + (n1 & 1u));
-#if defined(NW_KNOCKOUT) && NW_KNOCKOUT == 3   /* timing experiment: no Tm stores */
-            if (pk_lo(y.re) != (T)123.456) continue;
-#endif
-#if !defined(NW_TM_PACKED)   /* plain complex Tm: 8-byte stores that fill whole sectors; pass B repacks in its first pass */
             cx<T>* oc = x.col + e;
             oc[0] = lane0(y);
             if (x.two) oc[(size_t)1 << shB] = lane1(y);
-#else
-            o[0] = pk_lo(y.re);
-            o[2] = pk_lo(y.im);
-            if (x.two) {
-                o[(size_t)2 << shB] = pk_hi(y.re);
-                o[((size_t)2 << shB) + 2] = pk_hi(y.im);
-            }
-#endif
         }
     }
 };
 
 template <typename T> NW_HD size_t passA2_smem_bytes(int N1, int tpsh) { return ((size_t)N1 << tpsh) * sizeof(cx2<T>); }
 template <typename T> NW_HD size_t passB2_smem_bytes(int N2, int tpsh) { return ((size_t)N2 << tpsh) * sizeof(cx2<T>) + 16; }
+
+NW_HD int nw_floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }   // b > 0
+NW_HD int nw_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }  // b > 0
+
+// W_f(k) X[k] for the two columns k2, k2 + 1 of row k1s (signed: the band [rec.lo, rec.hi) is given in signed transform
+// bins j = k1s N2 + k2, which a resampled group's plan places around bin 0, i.e. wrapped around the ends of its
+// M-point spectrum; the data bin is j + rec.shift), times the group's equaliser
+template <typename T>
+NW_HD cx2<T> passA2_bins(const Long2Params<T>& P, const FreqRec& rec, int fi, const cx<T>* X, int k1s, int k2) {
+    const int j = k1s * P.N2 + k2;
+    cx<T> a = mk<T>((T)0, (T)0), b = a;
+    if (k2 < P.N2 && j >= rec.lo && j < rec.hi) {
+        a = spec_times<T>(P.sp, rec, fi, j + rec.shift, X[j + rec.shift]);
+        if (P.eq) a = scale(a, P.eq[j < 0 ? -j : j]);
+    }
+    if (k2 + 1 < P.N2 && j + 1 >= rec.lo && j + 1 < rec.hi) {
+        b = spec_times<T>(P.sp, rec, fi, j + 1 + rec.shift, X[j + 1 + rec.shift]);
+        if (P.eq) b = scale(b, P.eq[j + 1 < 0 ? -(j + 1) : j + 1]);
+    }
+    return mk2<T>(a, b);
+}
 
 // The tile's input - spectrum x signal spectrum on the non-zero band only - is gathered into the
 // transform's shared-memory slots by a compact loop (one evaluation per in-band bin, nothing unrolled
@@ -210,15 +184,14 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const int si = gr / P.F, fi = gr - si * P.F;
     const int N1 = P.N1, N2 = P.N2;
     const FreqRec rec = P.sp.rec[fi];
-    const cx<T>* X = P.X + (size_t)si * (size_t)P.N;
-    // rows k1 of this tile that hold a non-zero bin k = k1 N2 + k2, k2 in [c, c + 2 TP)
+    const cx<T>* X = P.X + (size_t)si * (size_t)P.xstride;
+    // signed rows k1s of this tile that hold a non-zero bin j = k1s N2 + k2, k2 in [c, c + 2 TP); the slot is k1s mod N1
     const int clast = (c + 2 * TP < N2 ? c + 2 * TP : N2) - 1;
-    int k1lo = rec.lo > clast ? (rec.lo - clast + N2 - 1) / N2 : 0;
-    int k1hi = rec.hi - 1 >= c ? (rec.hi - 1 - c) / N2 : -1;
-    if (k1hi > N1 - 1) k1hi = N1 - 1;
-    const int nk1 = k1hi - k1lo + 1;
-    first_wave_stagger<T>(P, bx, by, (N2 + 2 * TP - 1) / (2 * TP));
-    TmDst2<T> dst{&P, P.Tm + (size_t)(P.tm_mod > 0 ? by % P.tm_mod : by) * P.tm_stride, c, 1, fastdiv{1, 0}};
+    const int k1lo = nw_ceil_div(rec.lo - clast, N2);
+    int nk1 = nw_floor_div(rec.hi - 1 - c, N2) - k1lo + 1;
+    if (nk1 > N1) nk1 = N1;
+    if (rec.hi <= rec.lo || nk1 < 0) nk1 = 0;
+    TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c};
     typedef StaticPlan<SP> S;
     if constexpr (NARROW) {
         // Narrow band (it touches at most N1 / R rows): every butterfly of the first pass - inputs k1 = rev + q * step -
@@ -229,20 +202,19 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
             const int tp = i & (TP - 1);
             const int blk = i >> tpsh;
             const int rev = fft2_rev(P.stA, blk);
-            const int q = rev >= k1lo ? 0 : (int)fd_div((uint32_t)(k1lo - rev + step - 1), P.dstepA);
-            const int k1 = rev + q * step;
-            const int k2 = c + 2 * tp;
+            // the one row k1s = k1lo + u of the window with k1s = rev (mod step)
+            const uint32_t d = (uint32_t)(rev - k1lo + N1);                 // > 0: |k1lo| <= N1
+            const int u = (int)(d - fd_div(d, P.dstepA) * (uint32_t)step);
+            const bool ok = u < nk1;
             cx2<T>* e = buf + (((size_t)blk * rl) << tpsh) + tp;
-            const bool ok = nk1 > 0 && q < rl && k1 <= k1hi;
             cx2<T> y = zero2<T>();
             cx<T> wq = mk<T>((T)1, (T)0);
             if (ok) {
-                const int k = k1 * N2 + k2;
-                cx<T> a = mk<T>((T)0, (T)0), b = a;
-                if (k2 < N2 && k >= rec.lo && k < rec.hi) a = spec_times<T>(P.sp, rec, fi, k, X[k]);
-                if (k2 + 1 < N2 && k + 1 >= rec.lo && k + 1 < rec.hi) b = spec_times<T>(P.sp, rec, fi, k + 1, X[k + 1]);
-                y = mk2<T>(a, b);
-                wq = P.twA[q * step];
+                const int k1s = k1lo + u;
+                int k1 = k1s % N1;
+                if (k1 < 0) k1 += N1;
+                y = passA2_bins<T>(P, rec, fi, X, k1s, c + 2 * tp);
+                wq = P.twA[k1 - rev];                                       // q * step, q = k1 / step
             }
             e[0] = y;
 #pragma unroll 4
@@ -260,13 +232,10 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     NW_SYNC();
     for (int i = tid; i < (nk1 << tpsh); i += nthr) {
         const int tp = i & (TP - 1);
-        const int k1 = k1lo + (i >> tpsh);
-        const int k2 = c + 2 * tp;
-        const int k = k1 * N2 + k2;
-        cx<T> a = mk<T>((T)0, (T)0), b = a;
-        if (k2 < N2 && k >= rec.lo && k < rec.hi) a = spec_times<T>(P.sp, rec, fi, k, X[k]);
-        if (k2 + 1 < N2 && k + 1 >= rec.lo && k + 1 < rec.hi) b = spec_times<T>(P.sp, rec, fi, k + 1, X[k + 1]);
-        buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(a, b);
+        const int k1s = k1lo + (i >> tpsh);
+        int k1 = k1s % N1;
+        if (k1 < 0) k1 += N1;
+        buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1s, c + 2 * tp);
     }
     NW_SYNC();
     if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
@@ -291,65 +260,8 @@ NW_HD void passA2f_body(const Long2Params<T>& P, char* smem, int bx, int by, int
         buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(pk_make(a, b), pk_bcast((T)0));
     }
     NW_SYNC();
-    TmDst2<T, -1> dst{&P, P.Tm + (size_t)by * P.tm_stride, c, 1, fastdiv{1, 0}};
+    TmDst2<T, -1> dst{&P, P.Tm + (size_t)by * P.tm_stride, c};
     fft2_dit<T, -1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
-}
-
-// Pruned pass A.  A band that touches C <= n1b rows k1 gives every column a window of <= n1b consecutive k1;
-// with n1 = a + n1a b (n1a = N1 / n1b):   A[a + n1a b] = sum_j U_a[j] w_n1b^{j b},   U_a[k1 mod n1b] = Y[k1] w_N1^{k1 a}
-// - n1a transforms of length n1b per column instead of one of length N1 (log2 n1b levels instead of log2 N1).
-// The tile interleaves (column pair, phase a) sequences, a fastest, so natural-order results of neighbouring
-// lanes are consecutive rows n1 of the same column.
-template <typename T>
-NW_HD void passA2p_body(const Long2Params<T>& P, char* smem, int bx, int by, int tid, int nthr) {
-    cx2<T>* buf = (cx2<T>*)smem;
-    const int tpsh = P.tpshA, TP = 1 << tpsh;
-    const int c = bx << (tpsh + 1);
-    const int gr = P.row0 + by;
-    const int si = gr / P.F, fi = gr - si * P.F;
-    const int N1 = P.N1, N2 = P.N2;
-    const FreqRec rec = P.sp.rec[fi];
-    const PrunePlan& pp = P.pplans[rec.pad_];
-    const int n1a = pp.n1a, n1b = pp.st.P, nseq = pp.nseq;
-    const cx<T>* X = P.X + (size_t)si * (size_t)P.N;
-    const int clast = (c + 2 * TP < N2 ? c + 2 * TP : N2) - 1;
-    int k1lo = rec.lo > clast ? (rec.lo - clast + N2 - 1) / N2 : 0;
-    int k1hi = rec.hi - 1 >= c ? (rec.hi - 1 - c) / N2 : -1;
-    if (k1hi > N1 - 1) k1hi = N1 - 1;
-    const int nk1 = k1hi - k1lo + 1;   // <= n1b by construction of the plan
-    const cx2<T> z = zero2<T>();
-    for (int i = tid; i < (N1 << tpsh); i += nthr) buf[i] = z;
-    NW_SYNC();
-    // one thread per in-band (row k1, column pair): evaluate Y once, write its n1a phase-shifted copies
-    // U_a = Y w_N1^{k1 a}; the table index k1 a mod N1 is kept incrementally
-    for (int i = tid; i < (nk1 << tpsh); i += nthr) {
-        const int tp = i & (TP - 1);
-        const int k1 = k1lo + (i >> tpsh);
-        const int k2 = c + 2 * tp;
-        const int k = k1 * N2 + k2;
-        cx<T> a = mk<T>((T)0, (T)0), b = a;
-        if (k2 < N2 && k >= rec.lo && k < rec.hi) a = spec_times<T>(P.sp, rec, fi, k, X[k]);
-        if (k2 + 1 < N2 && k + 1 >= rec.lo && k + 1 < rec.hi) b = spec_times<T>(P.sp, rec, fi, k + 1, X[k + 1]);
-        const cx2<T> y = mk2<T>(a, b);
-        const int j = k1 - (int)fd_div((uint32_t)k1, pp.dn1b) * n1b;
-        cx2<T>* slot = buf + (size_t)fft2_dit_pos(pp.st, j) * nseq + tp * n1a;
-        slot[0] = y;
-        int idx = 0;
-#pragma unroll 2
-        for (int q = 1; q < n1a; ++q) {
-            idx += k1;
-            if (idx >= N1) idx -= N1;
-            slot[q] = cmul_s(y, P.twA[idx]);
-        }
-    }
-    NW_SYNC();
-    TmDst2<T> dst{&P, P.Tm + (size_t)by * P.tm_stride, c, n1a, pp.dn1a};
-    SeqDesc sq;
-    sq.tpsh = -1;
-    sq.nseq = nseq;
-    sq.twscale = n1a;
-    sq.d = pp.dseq;
-    fft2_dit<T, +1>(pp.st, sq, P.twA, buf, FromBuf(), dst, tid, nthr);
 }
 
 // ---- pass B --------------------------------------------------------------------------------
@@ -412,7 +324,7 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const int TB = 1 << shB;
     cx2<T>* buf = (cx2<T>*)smem;
     const size_t tile_elems = (size_t)P.N2 << shB;   // complex values
-    const cx<T>* tile = P.Tm + (size_t)(P.tm_mod > 0 ? by % P.tm_mod : by) * P.tm_stride + (size_t)bx * tile_elems;
+    const cx<T>* tile = P.Tm + (size_t)by * P.tm_stride + (size_t)bx * tile_elems;
 #if defined(__CUDA_ARCH__)
     const size_t bytes = tile_elems * sizeof(cx<T>);
     uint64_t* bar = (uint64_t*)((char*)smem + bytes);
@@ -427,20 +339,19 @@ NW_HD void passB2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         }
     }
     mbar_wait(bar, 0);
-    first_wave_stagger<T>(P, bx, by, (P.N1 + TB - 1) / TB);
 #else
     for (size_t i = tid; i < tile_elems; i += nthr) ((cx<T>*)smem)[i] = tile[i];
     NW_SYNC();
 #endif
-    const int gr = P.row0 + by;
+    size_t orow = (size_t)(P.row0 + by);
+    if (P.fmap) {   // frequency subset: launch row (si, fi) -> output row si * F_out + fmap[fi]
+        const int gr = P.row0 + by, si = gr / P.F;
+        orow = (size_t)si * (size_t)P.F_out + (size_t)P.fmap[gr - si * P.F];
+    }
     const size_t esz = (MODE == OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
-    LongOutDst2<T, MODE> dst{(char*)P.out + (size_t)gr * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
+    LongOutDst2<T, MODE> dst{(char*)P.out + orow * (size_t)P.N * esz, P.N1, bx * TB, (P.N1 & 1) == 0};
     typedef StaticPlan<SP> S;
-#if !defined(NW_TM_PACKED)
-    constexpr bool RAWT = true;
-#else
-    constexpr bool RAWT = false;
-#endif
+    constexpr bool RAWT = true;   // Tm holds plain complex values; the first pass repacks pairs of rows into lanes
     if constexpr (SP == 0) fft2_dif<T, DIR, RAWT>(P.stB, P.tpshB, P.twB, buf, dst, tid, nthr);
     else fft2_dif_static<T, DIR, RAWT, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twB, buf, dst, tid, nthr);
 }

@@ -6,6 +6,7 @@
 #include "nw_kernels.cuh"
 #include "nw_kernels2.cuh"
 #include "nw_kernels3.cuh"
+#include "nw_resample.cuh"
 
 namespace nw {
 template <typename T> cudaError_t prepare_short();
@@ -30,4 +31,9 @@ template <typename T> cudaError_t prepare_short2();
 template <typename T> bool has_static_short2(int sp);
 template <typename T>
 cudaError_t launch_short2(int sp, const Short2Params<T>& P, unsigned grid, int nthr, size_t smem, cudaStream_t s);
+// interpolation kernel of the resampled rows (nw_resample.cuh); K = taps, mode = OUT_ABS / OUT_POWER
+template <typename T> cudaError_t prepare_resample();
+template <typename T> bool has_resample(int K);
+template <typename T>
+cudaError_t launch_resample(int K, int mode, const ResampleParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
 }  // namespace nw

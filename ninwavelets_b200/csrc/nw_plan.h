@@ -13,10 +13,29 @@
 #include <vector>
 #include <algorithm>
 
+#include <memory>
+
 #include "nw_common.h"
 #include "nw_family.cuh"
 
 namespace nw {
+
+struct HostPlan;
+
+// A group of frequencies whose rows are computed at a reduced rate and interpolated ("resampled rows"):
+// the band of every row fits M = N / D bins with room to spare, so the inverse transform runs at length M on the band
+// moved to bin 0 (FreqRec::shift) and nw_resample.cuh interpolates the M samples to the N outputs with a K-tap
+// Kaiser-Bessel kernel whose pass-band response is divided out of the spectrum beforehand (eq).  D == 1: the group's rows
+// take the exact length-N transform.
+struct MrGroup {
+    int D = 1, K = 0;
+    double beta = 0, err = 0;          // kernel shape; worst-case relative error of an interpolated row, any input
+    std::vector<int> fidx;             // plan frequency index of each of the group's rows
+    std::shared_ptr<HostPlan> sub;     // plan of length N / D for those frequencies
+    std::vector<double> coef;          // [D][K] interpolation weights, phase-major
+    std::vector<int> t0;               // [D] offset of the first tap of each phase
+    std::vector<double> eq;            // D / H(j), j = 0 .. eq.size() - 1
+};
 
 static const size_t SMEM_MAX = 227 * 1024;       // opt-in dynamic shared memory per CTA (sm_100)
 static const size_t SMEM_HALF = 113 * 1024;      // two CTAs per SM
@@ -24,9 +43,13 @@ static const size_t SMEM_HALF = 113 * 1024;      // two CTAs per SM
 struct HostPlan {
     // description
     int device = 0, dtype = 0, family = 0, interpolate = 0;
-    long long N = 0;
+    long long N = 0;             // transform length
+    long long Nd = 0;            // data length: frequency grid, spectra pitch, 1/Nd normalisation (0: = N; a resampled group's plan: N * D)
     int F = 0;
     double sfreq = 0, p0 = 0, p1 = 0, p2 = 0, prune_eps = 0;
+    int resample = -1;           // < 0: library default (on), 0: exact transforms only
+    double resample_tol = 0;     // worst-case relative error allowed to the interpolation (0: default per dtype)
+    std::vector<MrGroup> groups; // empty: every row takes the exact transform
     std::vector<double> freqs, aux;
     std::vector<double> table;   // complex interleaved [F][table_len]
     long long table_len = 0;
@@ -60,11 +83,10 @@ struct HostPlan {
     int generic_ok = 1;          // long path: the generic two-pass kernels also have a plan for this N
     int narrowA = 0;             // every band touches <= N1 / R_last rows: pass A's first pass needs no loads (nw_kernels2.cuh)
     std::vector<char> narrow_ok; // the same per frequency: a launch group whose rows all qualify takes the narrow kernel
-    int pruneA = 0;              // pass A runs the pruned kernel (per-frequency PrunePlan, FreqRec::pad_)
-    std::vector<PrunePlan> pplans;
     size_t smem_A2 = 0, smem_B2 = 0;
     long long tm_stride2 = 0;
     int ring2 = 1;               // rows per pass-A / pass-B launch pair
+    long long data_len() const { return Nd > 0 ? Nd : N; }
 };
 
 inline size_t cx_size(int dtype) { return dtype == 0 ? 8 : 16; }
@@ -128,18 +150,6 @@ inline void fill_plan2(long long P, const std::vector<int>& rad, Fft2Plan& out) 
 }
 
 inline int env_int(const char* name, int dflt);
-
-// Two-pass plans with radix 24-32 butterflies (compile-time plans only, kernels of launch shapes 4 and 5);
-// opt-in: NWCWT_BIG bit 0 = pass B, bit 1 = pass A.
-inline bool plan_big(long long P, Fft2Plan& out) {
-    switch (P) {
-        case 1024: fill_plan2(P, {32, 32}, out); return true;
-        case 960: fill_plan2(P, {32, 30}, out); return true;
-        case 800: fill_plan2(P, {32, 25}, out); return true;
-        case 625: fill_plan2(P, {25, 25}, out); return true;
-        default: return false;
-    }
-}
 
 inline bool plan_packed(long long P, Fft2Plan& out) {
     if (P < 2 || P > (1 << 16)) return false;
@@ -205,15 +215,16 @@ inline long long arange_len(double total, double one) {
 }
 
 inline void plan_geometry(HostPlan& hp) {
-    const double L = (double)hp.N / hp.sfreq;   // wave.shape[0] / self.sfreq, base.py:395
+    const long long N = hp.data_len();
+    const double L = (double)N / hp.sfreq;      // wave.shape[0] / self.sfreq, base.py:395
     const double one = 1 / L;                    // base.py:192
     hp.df = one;
-    hp.cut = hp.N;
+    hp.cut = N;
     hp.grid_off = 0;
     if (hp.family == FAM_TABLE) {
         // pad_to, base.py:75-82: truncate, or centre with the short half in front
         hp.n_eval = hp.table_len;
-        if (hp.interpolate) hp.cut = hp.N / 2;   // interpolate_alias, base.py:121
+        if (hp.interpolate) hp.cut = N / 2;   // interpolate_alias, base.py:121
         return;
     }
     if (hp.interpolate) {
@@ -222,13 +233,13 @@ inline void plan_geometry(HostPlan& hp) {
         const double total = hp.sfreq / L * (L / 2);
         const long long half = arange_len(total, one);
         long long len = 2 * half;
-        hp.grid_off = len >= hp.N ? 0 : (int)((hp.N - len) / 2);
+        hp.grid_off = len >= N ? 0 : (int)((N - len) / 2);
         hp.n_eval = half;
-        hp.cut = hp.N / 2;
+        hp.cut = N / 2;
     } else {
         const double total = hp.sfreq / L * L;   // base.py:193, 244-245
         const long long len = arange_len(total, one);
-        hp.grid_off = len >= hp.N ? 0 : (int)((hp.N - len) / 2);
+        hp.grid_off = len >= N ? 0 : (int)((N - len) / 2);
         hp.n_eval = len;
     }
 }
@@ -303,6 +314,7 @@ inline void analytic_band(const HostPlan& hp, int fi, double eps, long long& glo
 }
 
 inline void plan_bands(HostPlan& hp) {
+    const long long N = hp.data_len();
     hp.rec.resize(hp.F);
     hp.band_bins = 0;
     for (int i = 0; i < hp.F; ++i) {
@@ -312,21 +324,23 @@ inline void plan_bands(HostPlan& hp) {
         r.kx = hp.family == FAM_MORLET ? hp.df / r.freq * r.aux : hp.df / r.freq;
         long long lo, hi;
         r.toff = 0;
-        r.pad_ = 0;
+        r.shift = 0;
         if (hp.family == FAM_TABLE) {
             // pad_to, base.py:75-82: truncate, or centre with the short half in front
             const long long m = hp.table_lens.empty() ? hp.table_len : hp.table_lens[i];
-            r.toff = m >= hp.N ? 0 : (int)((hp.N - m) / 2);
+            r.toff = m >= N ? 0 : (int)((N - m) / 2);
             lo = r.toff;
-            hi = r.toff + std::min(m, hp.N);
+            hi = r.toff + std::min(m, N);
+            // interpolate_alias is applied to the table at ITS length before pad_to (base.py:276, 121-123)
+            if (hp.interpolate) hi = std::min(hi, r.toff + m / 2);
         } else {
             long long glo, ghi;
             analytic_band(hp, i, hp.prune_eps, glo, ghi);
             lo = glo + hp.grid_off;
             hi = ghi + hp.grid_off;
         }
-        lo = std::max(0LL, std::min(lo, hp.N));
-        hi = std::max(lo, std::min(std::min(hi, hp.N), hp.cut));
+        lo = std::max(0LL, std::min(lo, N));
+        hi = std::max(lo, std::min(std::min(hi, N), hp.cut));
         lo = std::min(lo, hi);
         r.lo = (int)lo;
         r.hi = (int)hi;
@@ -343,10 +357,10 @@ inline int ilog2_floor(long long v) { int l = 0; while ((1LL << (l + 1)) <= v) +
 // take the multiple of 32 that wastes the fewest thread slots over all stages, weighted by how many
 // threads the shape keeps resident per SM (shared memory and registers), with a small bonus for the
 // shape with more registers per thread.
-static const int N_CFG2 = 6;
-static const int CFG2_MAXTHR[N_CFG2] = {256, 224, 128, 64, 128, 128};
-static const int CFG2_MINCTA[N_CFG2] = {3, 3, 5, 8, 2, 3};
-static const int CFG2_MAXREG[N_CFG2] = {80, 96, 96, 128, 255, 168};   // __maxnreg__ of the compiled kernels
+static const int N_CFG2 = 4;
+static const int CFG2_MAXTHR[N_CFG2] = {256, 224, 128, 64};
+static const int CFG2_MINCTA[N_CFG2] = {3, 3, 5, 8};
+static const int CFG2_MAXREG[N_CFG2] = {80, 96, 96, 128};   // __maxnreg__ of the compiled kernels
 inline int cfg2_regcap(int c) { return CFG2_MAXREG[c]; }
 
 inline void pick_threads2(const Fft2Plan& st, int tpsh, size_t smem, int ncfg, int& nthr, int& cfg) {
@@ -385,11 +399,10 @@ inline void pick_threads2(const Fft2Plan& st, int tpsh, size_t smem, int ncfg, i
 
 inline int env_int(const char* name, int dflt);
 
-// Pruned pass A: per frequency the shortest packed-plannable divisor n1b of N1 that holds the rows k1 the band
-// touches.  Enabled when it shortens the column transform for at least half of the frequencies.
-inline void plan_prune(HostPlan& hp) {
-    hp.pruneA = 0;
-    hp.pplans.clear();
+// Narrow-band first pass of pass A (nw_kernels2.cuh): allowed for a frequency whose band touches at most
+// N1 / R_last rows of any column tile.
+inline long long floor_div_ll(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+inline void plan_narrow(HostPlan& hp) {
     hp.narrowA = 0;
     hp.narrow_ok.clear();
     if (hp.fast && hp.F > 0 && hp.stA2.nst >= 2 && !env_int("NWCWT_NO_NARROW", 0)) {
@@ -399,46 +412,12 @@ inline void plan_prune(HostPlan& hp) {
         for (int i = 0; i < hp.F; ++i) {
             const FreqRec& r = hp.rec[i];
             // rows a tile of 2 << tpshA columns can touch: one more than the band's own row span
-            const int C = r.hi > r.lo ? (r.hi - 1) / hp.N2f - r.lo / hp.N2f + 2 : 0;
+            const int C = r.hi > r.lo ? (int)(floor_div_ll(r.hi - 1, hp.N2f) - floor_div_ll(r.lo, hp.N2f)) + 2 : 0;
             worst = std::max(worst, C);
             hp.narrow_ok[(size_t)i] = C <= step;
         }
         hp.narrowA = worst <= step;
     }
-    // r01 measurement (profiles/r01/shape_sweep.md): with run-time plans the pruned kernel executes as many
-    // instructions as the unpruned compile-time-plan kernel and stalls on its phase-table loads (22.6 vs
-    // 15.4 ms per cfg2 step), so it is opt-in (NWCWT_PRUNE=1) until it has compile-time plans of its own.
-    if (!hp.fast || hp.F <= 0 || !env_int("NWCWT_PRUNE", 0)) return;
-    const int N1 = hp.N1f, N2 = hp.N2f, TP = 1 << hp.tpshA;
-    std::vector<int> cand;
-    for (int d = 2; d <= N1; ++d) {
-        Fft2Plan t;
-        if (N1 % d == 0 && plan_packed(d, t)) cand.push_back(d);
-    }
-    std::vector<int> idx_of(N1 + 1, -1);
-    int shorter = 0;
-    for (int i = 0; i < hp.F; ++i) {
-        FreqRec& r = hp.rec[i];
-        const int C = r.hi > r.lo ? (r.hi - 1) / N2 - r.lo / N2 + 1 : 1;
-        int n1b = N1;
-        for (int d : cand) if (d >= C) { n1b = d; break; }
-        if (n1b < N1) ++shorter;
-        if (idx_of[n1b] < 0) {
-            PrunePlan pp;
-            memset(&pp, 0, sizeof(pp));
-            plan_packed(n1b, pp.st);
-            pp.n1a = N1 / n1b;
-            pp.nseq = TP * pp.n1a;
-            pp.dseq = make_fastdiv((uint32_t)pp.nseq);
-            pp.dn1a = make_fastdiv((uint32_t)pp.n1a);
-            pp.dn1b = make_fastdiv((uint32_t)n1b);
-            pp.dn1a1 = make_fastdiv((uint32_t)std::max(1, pp.n1a - 1));
-            idx_of[n1b] = (int)hp.pplans.size();
-            hp.pplans.push_back(pp);
-        }
-        r.pad_ = idx_of[n1b];
-    }
-    hp.pruneA = 2 * shorter >= hp.F;
 }
 
 // May the launch group of rows [r0, r0 + g) (row = signal * F + frequency) use the narrow-band first pass of pass A?
@@ -473,8 +452,6 @@ inline void plan_shape_fast(HostPlan& hp) {
             if (env_int("NWCWT_SPLIT_N1", 0) > 0 && n1 != env_int("NWCWT_SPLIT_N1", 0)) continue;   // tuning override
             Fft2Plan a, b;
             if (!plan_packed(n1, a) || !plan_packed(n2, b)) continue;
-            if (hp.dtype == 0 && (env_int("NWCWT_BIG", 0) & 2)) plan_big(n1, a);   // fp32 kernels only
-            if (hp.dtype == 0 && (env_int("NWCWT_BIG", 0) & 1)) plan_big(n2, b);
             const int fa = env_int("NWCWT_TPSH_A", -1), fb = env_int("NWCWT_TPSH_B", -1);   // tuning overrides
             for (int ta = 2; ta >= 0; --ta)
                 for (int tb = 2; tb >= 0; --tb) {
@@ -506,7 +483,7 @@ inline void plan_shape_fast(HostPlan& hp) {
         }
     }
     if (!hp.fast) return;
-    const int ncfg = hp.dtype == 0 ? 4 : 1;   // fp64 kernels exist in shape 0 only; shapes 4, 5 are opt-in
+    const int ncfg = hp.dtype == 0 ? 4 : 1;   // fp64 kernels exist in shape 0 only
     pick_threads2(hp.stA2, hp.tpshA, hp.smem_A2, ncfg, hp.nthrA2, hp.cfgA);
     pick_threads2(hp.stB2, hp.tpshB, hp.smem_B2, ncfg, hp.nthrB2, hp.cfgB);
     if (hp.dtype == 1) {   // fp64 kernels: 168 registers, three 128-thread CTAs per SM (measured: +6 % cfg2, +20 % 2^20 over 256 x 2 at 128)
@@ -528,12 +505,6 @@ inline void plan_shape_fast(HostPlan& hp) {
         hp.cfgA = env_int("NWCWT_CFG_A", hp.cfgA);
         hp.cfgB = env_int("NWCWT_CFG_B", hp.cfgB);
     }
-    // radix 25-32 plans exist in the launch shapes 4 and 5 only (128 threads, 2 or 3 CTAs per SM)
-    auto big = [](const Fft2Plan& p) { for (int i = 0; i < p.nst; ++i) if (p.radix[i] > 20) return true; return false; };
-    if (big(hp.stA2) && hp.cfgA < 4) hp.cfgA = 5;
-    if (big(hp.stB2) && hp.cfgB < 4) hp.cfgB = 5;
-    if (hp.cfgA >= 4) hp.nthrA2 = std::min(hp.nthrA2, CFG2_MAXTHR[hp.cfgA]);
-    if (hp.cfgB >= 4) hp.nthrB2 = std::min(hp.nthrB2, CFG2_MAXTHR[hp.cfgB]);
     const int TB = 2 << hp.tpshB;
     const long long nblk = (hp.N1f + TB - 1) / TB;
     hp.tm_stride2 = nblk * hp.N2f * TB;
@@ -571,6 +542,8 @@ inline void plan_shape_short2(HostPlan& hp) {
     hp.nthrS2 = (int)std::min<long long>(256, std::max<long long>(64, (maxnb + 31) / 32 * 32));
     hp.nthrS2 = env_int("NWCWT_NTHR_S", hp.nthrS2);
 }
+
+inline void plan_multirate(HostPlan& hp);
 
 inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) {
     const size_t cs = cx_size(hp.dtype);
@@ -636,7 +609,8 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
         // only the packed kernels can take this length (tiles too large for the generic engine's two buffers)
         hp.generic_ok = 0;
         hp.ring = (int)std::max<long long>(1, std::min<long long>(64, (256LL << 20) / (N * (long long)cs)));
-        plan_prune(hp);
+        plan_narrow(hp);
+        plan_multirate(hp);
         return true;
     }
     hp.N1 = (int)best1;
@@ -652,8 +626,256 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
     const size_t slot = (size_t)hp.tm_stride * cs;
     long long ring = (long long)((48u << 20) / slot);
     hp.ring = (int)std::max<long long>(1, std::min<long long>(ring, 64));
-    plan_prune(hp);
+    plan_narrow(hp);
+    plan_multirate(hp);
     return true;
+}
+
+
+// ---- resampled rows ---------------------------------------------------------------------------------------
+// A row whose band [lo, hi) holds B bins is band limited: its N samples are determined by M >= B of them.  With
+// M = N / D the decimated row  y[m] = z(m D) e^{-2 pi i kc m / M}  (kc = band centre) is the M-point inverse transform
+// of the band moved to bin 0, and  |z(m D + p)| = | sum_t phi(p / D - (t0_p + t)) y[m + t0_p + t] |  up to the images
+// of the band that the interpolation kernel phi lets through.  phi is a Kaiser-Bessel window of K taps; its own
+// frequency response H is divided out of the spectrum (MrGroup::eq), so the pass band is exact and the error of a row
+// is bounded - for ANY input - by  max_j sqrt(sum_{r != 0} |H(j + r M)|^2) / |H(j)|  over the band, which the planner
+// evaluates for the kernel it picks (MrGroup::err) and keeps below resample_tol.
+
+inline double bessel_i0(double x) {   // power series; x <= ~60 here
+    const double q = 0.25 * x * x;
+    double t = 1.0, s = 1.0;
+    for (int k = 1; k < 500; ++k) {
+        t *= q / ((double)k * (double)k);
+        s += t;
+        if (t < 1e-18 * s) break;
+    }
+    return s;
+}
+
+// phi(tau), |tau| <= K / 2: (I0(beta sqrt(1 - (2 tau / K)^2)) - 1) / (I0(beta) - 1), zero at the ends of its support
+inline double kb_phi(double tau, int K, double beta, double inv_i0m1) {
+    const double u = 2.0 * tau / (double)K, a = 1.0 - u * u;
+    if (!(a > 0.0)) return 0.0;
+    return (bessel_i0(beta * sqrt(a)) - 1.0) * inv_i0m1;
+}
+
+// H(j) = sum_i phi(i / D) cos(2 pi j i / (M D)) for the listed bins j (signed, any size)
+inline void kb_response(int D, int K, double beta, long long M, const std::vector<long long>& bins, std::vector<double>& H) {
+    const long long half = (long long)K * D / 2;
+    const double inv = 1.0 / (bessel_i0(beta) - 1.0);
+    std::vector<double> h((size_t)half + 1);
+    for (long long i = 0; i <= half; ++i) h[(size_t)i] = kb_phi((double)i / (double)D, K, beta, inv);
+    const long long Nf = M * (long long)D;
+    const long double tp = 6.283185307179586476925286766559005768L;
+    H.resize(bins.size());
+    for (size_t b = 0; b < bins.size(); ++b) {
+        long long j = bins[b] % Nf;
+        if (j < 0) j += Nf;
+        const double th = (double)(tp * (long double)j / (long double)Nf);
+        // cos(i th) by the Chebyshev recurrence, restarted from an exact value every 64 terms
+        double acc = h[0];
+        for (long long i0 = 1; i0 <= half; i0 += 64) {
+            const long long i1 = std::min(half, i0 + 63);
+            double c0 = cos((double)(i0 - 1) * th), c1 = cos((double)i0 * th);
+            const double k2 = 2.0 * cos(th);
+            for (long long i = i0; i <= i1; ++i) {
+                acc += 2.0 * h[(size_t)i] * c1;
+                const double c2 = k2 * c1 - c0;
+                c0 = c1;
+                c1 = c2;
+            }
+        }
+        H[b] = acc;
+    }
+}
+
+// worst-case relative error of the K-tap kernel for a band of half width jmax (bins) at decimation D of N = M D
+inline double kb_worst_error(int D, int K, double beta, long long M, long long jmax) {
+    if (D < 2) return 0.0;
+    std::vector<long long> bins;
+    const int NP = 9;   // the error grows towards the band edge; sample the outer fifth and the centre
+    std::vector<long long> js;
+    for (int i = 0; i < NP; ++i) js.push_back(jmax - (long long)((double)jmax * 0.2 * (double)i / (double)(NP - 1)));
+    js.push_back(0);
+    for (long long j : js)
+        for (int r = 0; r < D; ++r) bins.push_back(j + (long long)r * M);
+    std::vector<double> H;
+    kb_response(D, K, beta, M, bins, H);
+    double worst = 0.0;
+    for (size_t a = 0; a < js.size(); ++a) {
+        double al = 0.0;
+        for (int r = 1; r < D; ++r) al += H[a * D + r] * H[a * D + r];
+        const double main = fabs(H[a * D]);
+        worst = std::max(worst, main > 0 ? sqrt(al) / main : 1e300);
+    }
+    return worst;
+}
+
+// smallest K (and its beta) whose worst-case error is <= tol; false if none up to kmax
+inline bool kb_design(int D, long long M, long long jmax, double tol, int kmax, bool even, int& K, double& beta, double& err) {
+    const double os = (double)M / (2.0 * (double)std::max<long long>(jmax, 1));
+    if (os <= 1.02) return false;
+    const double PI = 3.14159265358979323846;
+    // estimate: error ~ 2 y exp(-y), y = pi K sqrt(1 - 1/os)  (about 3x pessimistic)
+    int k0 = 4;
+    for (; k0 < kmax; ++k0) {
+        const double y = PI * k0 * sqrt(1.0 - 1.0 / os);
+        if (2.0 * y * exp(-y) <= 4.0 * tol) break;
+    }
+    for (int k = std::max(even ? 8 : 4, k0 - 2); k <= kmax; ++k) {
+        if (even && (k & 1)) continue;   // the fp64 kernels are compiled for even tap counts
+        double best = 1e300, bb = 0;
+        for (double f = 0.94; f <= 1.005; f += 0.02) {
+            const double b = f * PI * k * (1.0 - 0.5 / os);
+            const double e = kb_worst_error(D, k, b, M, jmax);
+            if (e < best) { best = e; bb = b; }
+        }
+        if (best <= tol) { K = k; beta = bb; err = best; return true; }
+    }
+    return false;
+}
+
+inline void plan_shape_fast(HostPlan& hp);
+
+// Build the plan of a frequency subset at length M = N / D (D == 1: the exact transform of that subset).
+inline std::shared_ptr<HostPlan> make_sub_plan(const HostPlan& hp, const std::vector<int>& fidx, int D) {
+    std::shared_ptr<HostPlan> sp = std::make_shared<HostPlan>();
+    HostPlan& s = *sp;
+    s.device = hp.device; s.dtype = hp.dtype; s.family = hp.family; s.interpolate = hp.interpolate;
+    s.N = hp.N / D;
+    s.Nd = hp.N;
+    s.F = (int)fidx.size();
+    s.sfreq = hp.sfreq; s.p0 = hp.p0; s.p1 = hp.p1; s.p2 = hp.p2; s.prune_eps = hp.prune_eps;
+    s.resample = 0;
+    for (int i : fidx) {
+        s.freqs.push_back(hp.freqs[(size_t)i]);
+        if (!hp.aux.empty()) s.aux.push_back(hp.aux[(size_t)i]);
+        if (!hp.table_lens.empty()) s.table_lens.push_back(hp.table_lens[(size_t)i]);
+    }
+    if (hp.family == FAM_TABLE) {
+        s.table_len = hp.table_len;
+        s.table.reserve(2 * fidx.size() * (size_t)hp.table_len);
+        for (int i : fidx)
+            s.table.insert(s.table.end(), hp.table.begin() + 2 * (size_t)i * (size_t)hp.table_len,
+                           hp.table.begin() + 2 * ((size_t)i + 1) * (size_t)hp.table_len);
+    }
+    plan_geometry(s);
+    plan_bands(s);
+    if (D > 1)
+        for (FreqRec& r : s.rec) {   // centre the band on transform bin 0
+            const int kc = r.lo + (r.hi - r.lo) / 2;
+            r.shift = kc;
+            r.lo -= kc;
+            r.hi -= kc;
+        }
+    s.path = 1;
+    s.lb = (ilog2_floor(s.N) + 2) / 2;
+    s.generic_ok = 0;
+    plan_shape_fast(s);
+    if (!s.fast) return nullptr;
+    plan_narrow(s);
+    return sp;
+}
+
+// cost model, picoseconds per OUTPUT sample on B200 (profiles/r02: measured engine rate and interpolation kernel)
+struct MrCost { double engine, fir0, fir_tap; };
+inline MrCost mr_cost(int dtype) { return dtype == 0 ? MrCost{5.8, 0.8, 0.09} : MrCost{17.0, 1.6, 0.3}; }
+
+inline void plan_multirate(HostPlan& hp) {
+    hp.groups.clear();
+    if (hp.path != 1 || !hp.fast || hp.F <= 0 || hp.resample == 0 || hp.Nd > 0) return;
+    if (env_int("NWCWT_NO_RESAMPLE", 0)) return;
+    const long long N = hp.N;
+    const double tol = hp.resample_tol > 0 ? hp.resample_tol : (hp.dtype == 0 ? 5e-7 : 5e-14);
+    const int kmax = hp.dtype == 0 ? 16 : 24;   // tap counts the kernels are compiled for: 4..16 (fp32), 8, 10 .. 24 (fp64)
+    // shortest decimated length: below it the engine's tiles are too small to pay (tests lower it to reach the path on
+    // lengths the host emulation can afford)
+    long long MMIN = env_int("NWCWT_RESAMPLE_MMIN", 16384);
+    if (MMIN < 64) MMIN = 64;
+    const MrCost cm = mr_cost(hp.dtype);
+    // candidate decimations: divisors D of N with a fast plan at N / D
+    struct Cand { int D; long long M; };
+    std::vector<Cand> cands;
+    for (int D = 2; D <= 64; ++D) {
+        if (N % D || N / D < MMIN) continue;
+        HostPlan t;
+        t.dtype = hp.dtype; t.N = N / D; t.F = 1;
+        plan_shape_fast(t);
+        if (t.fast) cands.push_back(Cand{D, N / D});
+    }
+    if (cands.empty()) return;
+    // per frequency: the cheapest decimation whose kernel meets the tolerance
+    std::vector<int> pickD((size_t)hp.F, 1);
+    struct Key { int D; long long jmax; };
+    for (int i = 0; i < hp.F; ++i) {
+        const FreqRec& r = hp.rec[(size_t)i];
+        const long long B = (long long)r.hi - r.lo;
+        if (B <= 0) { pickD[(size_t)i] = cands.back().D; continue; }   // empty band: zero row, cheapest group
+        const long long jmax = B - B / 2;
+        double best = cm.engine * 0.92;   // switch only for a clear gain
+        for (const Cand& c : cands) {
+            if (2 * jmax * 51 > c.M * 50) continue;   // oversampling >= 1.02
+            int K; double beta, err;
+            // the estimate of kb_design's first loop is enough to rank; the group's kernel is verified below
+            const double os = (double)c.M / (2.0 * (double)jmax);
+            const double PI = 3.14159265358979323846;
+            int k = 4;
+            for (; k <= kmax; ++k) {
+                const double y = PI * k * sqrt(1.0 - 1.0 / os);
+                if (2.0 * y * exp(-y) <= 3.0 * tol) break;
+            }
+            if (k > kmax) continue;
+            (void)K; (void)beta; (void)err;
+            const double cost = cm.engine / c.D + cm.fir0 + cm.fir_tap * k;
+            if (cost < best) { best = cost; pickD[(size_t)i] = c.D; }
+        }
+    }
+    bool any = false;
+    for (int d : pickD) any = any || d > 1;
+    if (!any) return;
+    // groups by decimation, exact rows (D = 1) last
+    std::vector<int> Ds;
+    for (const Cand& c : cands) Ds.push_back(c.D);
+    std::sort(Ds.begin(), Ds.end(), [](int a, int b) { return a > b; });
+    Ds.push_back(1);
+    for (size_t di = 0; di < Ds.size(); ++di) {
+        const int D = Ds[di];
+        MrGroup g;
+        g.D = D;
+        for (int i = 0; i < hp.F; ++i) if (pickD[(size_t)i] == D) g.fidx.push_back(i);
+        if (g.fidx.empty()) continue;
+        g.sub = make_sub_plan(hp, g.fidx, D);
+        bool ok = (bool)g.sub;
+        if (ok && D > 1) {
+            long long jmax = 1;
+            for (const FreqRec& r : g.sub->rec) jmax = std::max<long long>(jmax, std::max<long long>(-(long long)r.lo, (long long)r.hi));
+            ok = kb_design(D, N / D, jmax, tol, kmax, hp.dtype == 1, g.K, g.beta, g.err);
+            if (ok) {
+                const double inv = 1.0 / (bessel_i0(g.beta) - 1.0);
+                g.coef.resize((size_t)D * g.K);
+                g.t0.resize((size_t)D);
+                for (int p = 0; p < D; ++p) {
+                    const double x = (double)p / (double)D;
+                    const int t0 = (int)floor(x - 0.5 * g.K) + 1;
+                    g.t0[(size_t)p] = t0;
+                    for (int t = 0; t < g.K; ++t) g.coef[(size_t)p * g.K + t] = kb_phi(x - (double)(t0 + t), g.K, g.beta, inv);
+                }
+                std::vector<long long> bins((size_t)jmax + 1);
+                for (long long j = 0; j <= jmax; ++j) bins[(size_t)j] = j;
+                std::vector<double> H;
+                kb_response(D, g.K, g.beta, N / D, bins, H);
+                g.eq.resize(H.size());
+                for (size_t j = 0; j < H.size(); ++j) g.eq[j] = (double)D / H[j];
+            }
+        }
+        if (!ok) {   // fall back to the exact transform for these rows: merge into the D = 1 group (built last)
+            if (D == 1) { hp.groups.clear(); return; }
+            for (int i : g.fidx) pickD[(size_t)i] = 1;
+            continue;
+        }
+        hp.groups.push_back(std::move(g));
+    }
+    if (hp.groups.size() == 1 && hp.groups[0].D == 1) hp.groups.clear();   // nothing resampled after all
 }
 
 }  // namespace nw

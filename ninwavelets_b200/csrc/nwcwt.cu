@@ -72,12 +72,8 @@ __global__ void __launch_bounds__(256) nwcwt_reduce_kernel(const void* in, T* ou
 // ---------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static bool g_no_static = getenv("NWCWT_NO_STATIC") != nullptr;   // tuning: run-time plans only
-static bool g_fwd_generic = getenv("NWCWT_FWD_GENERIC") != nullptr;   // tuning: forward transform on the generic kernels
-static int env_i(const char* n, int d) { const char* e = getenv(n); return e && *e ? atoi(e) : d; }
-static int g_skew_a = env_i("NWCWT_SKEW_A", 0), g_skew_mod_a = env_i("NWCWT_SKEW_MOD_A", 5);
-static int g_skew_b = env_i("NWCWT_SKEW_B", 0), g_skew_mod_b = env_i("NWCWT_SKEW_MOD_B", 3);
-static int g_tm_mod = env_i("NWCWT_TM_MOD", 0);   // timing experiment: wrong results
 static bool g_force_generic = false;   // nwcwt_debug_force_generic: run the generic kernels even where a fast path exists
+static bool g_exact = false;           // nwcwt_debug_force_exact: exact length-N transforms for every row of a resampling plan
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -95,7 +91,15 @@ struct nwcwt_plan {
     // device tables
     void *d_tw = nullptr, *d_twA = nullptr, *d_twB = nullptr, *d_twH = nullptr, *d_twL = nullptr;
     void *d_twA2 = nullptr, *d_twB2 = nullptr;   // fast long path
-    void* d_pplans = nullptr;                    // pruned pass A: PrunePlan[]
+    // resampled rows (HostPlan::groups): one sub-plan per group, plus the group's interpolation tables
+    struct Group {
+        nwcwt_plan* sub = nullptr;
+        void *d_coef = nullptr, *d_eq = nullptr;
+        int *d_t0 = nullptr, *d_fmap = nullptr;
+        int t0min = 0;
+    };
+    std::vector<Group> groups;
+    bool is_sub = false;
     // fast long path: launch pairs of consecutive row groups alternate between auxiliary streams so
     // that one group's pass A fills the SMs the previous group's pass-B tail leaves idle
     static const int MAX_AUX = 4;
@@ -127,8 +131,9 @@ static bool g_profile = false;
 static std::mutex g_prof_mu;
 struct ProfEvent { cudaEvent_t a, b; int cls; };
 static std::vector<ProfEvent> g_prof_events;
-static double g_prof_ms[6] = {0, 0, 0, 0, 0, 0};
-static long long g_prof_n[6] = {0, 0, 0, 0, 0, 0};
+static const int N_PROF = 8;
+static double g_prof_ms[N_PROF] = {0};
+static long long g_prof_n[N_PROF] = {0};
 
 struct LaunchScope {   // counts one launch; with profiling on, brackets it with events on `stream`
     cudaStream_t stream;
@@ -169,8 +174,7 @@ static void fill_twiddles(std::vector<cx<T>>& v, long long count, long long P, l
 template <typename T> struct Long2Dispatch;
 #define NW_BY_CFG(c, F, ...) \
     switch (c) { case 1: return F<float, 1>(__VA_ARGS__); case 2: return F<float, 2>(__VA_ARGS__); \
-                 case 3: return F<float, 3>(__VA_ARGS__); case 4: return F<float, 4>(__VA_ARGS__); \
-                 case 5: return F<float, 5>(__VA_ARGS__); default: return F<float, 0>(__VA_ARGS__); }
+                 case 3: return F<float, 3>(__VA_ARGS__); default: return F<float, 0>(__VA_ARGS__); }
 template <> struct Long2Dispatch<float> {
     static cudaError_t prepare(int c) { NW_BY_CFG(c, prepare_long2) }
     static bool has(int c, int pass, int sp) { NW_BY_CFG(c, has_static_plan, pass, sp) }
@@ -220,10 +224,6 @@ static int ensure_device_t(nwcwt_plan* pl) {
         if (hp.fast) {
             if ((rc = upload_tw<T>(&pl->d_twA2, hp.N1f, hp.N1f, 1))) return rc;
             if ((rc = upload_tw<T>(&pl->d_twB2, hp.N2f, hp.N2f, 1))) return rc;
-            if (!hp.pplans.empty()) {
-                CUDA_TRY(cudaMalloc(&pl->d_pplans, sizeof(PrunePlan) * hp.pplans.size()));
-                CUDA_TRY(cudaMemcpy(pl->d_pplans, hp.pplans.data(), sizeof(PrunePlan) * hp.pplans.size(), cudaMemcpyHostToDevice));
-            }
         }
     }
     if (hp.F > 0) {
@@ -260,8 +260,8 @@ static int ensure_device_t(nwcwt_plan* pl) {
                 pl->l2_window_max = (size_t)(v > 0 ? v : 0);
                 if (pl->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, pl->l2_persist_max);
             }
-            int ns = 2;
-            if (const char* e = getenv("NWCWT_STREAMS")) ns = atoi(e);
+            int ns = pl->is_sub ? 1 : 2;
+            if (const char* e = getenv("NWCWT_STREAMS")) ns = pl->is_sub ? 1 : atoi(e);
             ns = ns < 1 ? 1 : ns > nwcwt_plan::MAX_AUX ? nwcwt_plan::MAX_AUX : ns;
             if (ns > 1) {
                 for (int i = 0; i < ns; ++i) {
@@ -273,6 +273,26 @@ static int ensure_device_t(nwcwt_plan* pl) {
             }
         }
     }
+    // resampled groups: their sub-plans' tables and the interpolation tables
+    for (size_t gi = 0; gi < pl->groups.size(); ++gi) {
+        nwcwt_plan::Group& g = pl->groups[gi];
+        const MrGroup& mg = hp.groups[gi];
+        if ((rc = ensure_device_t<T>(g.sub))) return rc;
+        CUDA_TRY(cudaMalloc((void**)&g.d_fmap, sizeof(int) * mg.fidx.size()));
+        CUDA_TRY(cudaMemcpy(g.d_fmap, mg.fidx.data(), sizeof(int) * mg.fidx.size(), cudaMemcpyHostToDevice));
+        if (mg.D > 1) {
+            if (!has_resample<T>(mg.K)) return fail(NWCWT_ERR_UNSUPPORTED, "no interpolation kernel for this tap count");
+            std::vector<T> c(mg.coef.begin(), mg.coef.end()), e(mg.eq.begin(), mg.eq.end());
+            CUDA_TRY(cudaMalloc(&g.d_coef, sizeof(T) * c.size()));
+            CUDA_TRY(cudaMemcpy(g.d_coef, c.data(), sizeof(T) * c.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMalloc(&g.d_eq, sizeof(T) * e.size()));
+            CUDA_TRY(cudaMemcpy(g.d_eq, e.data(), sizeof(T) * e.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMalloc((void**)&g.d_t0, sizeof(int) * mg.t0.size()));
+            CUDA_TRY(cudaMemcpy(g.d_t0, mg.t0.data(), sizeof(int) * mg.t0.size(), cudaMemcpyHostToDevice));
+            g.t0min = *std::min_element(mg.t0.begin(), mg.t0.end());
+        }
+    }
+    if (!pl->groups.empty()) CUDA_TRY(prepare_resample<T>());
     pl->on_device = true;
     return 0;
 }
@@ -291,7 +311,7 @@ static SpecParams<T> make_spec(const nwcwt_plan* pl) {
     sp.p0 = hp.p0;
     sp.p1 = hp.p1;
     sp.p2 = hp.family == FAM_MORSE ? hp.p0 / hp.p1 : hp.p2;   // (self.b / self.r), wavelets.py:72
-    sp.norm = (T)(1.0 / (double)hp.N);                          // 1/N of ifft, base.py:406
+    sp.norm = (T)(1.0 / (double)hp.data_len());                 // 1/N of ifft, base.py:406
     sp.rec = (const FreqRec*)pl->d_rec;
     sp.table = (const cx<T>*)pl->d_table;
     sp.table_len = hp.table_len;
@@ -407,20 +427,32 @@ static LongParams<T> make_long(nwcwt_plan* pl) {
 }
 
 // intermediate ring of the long path: the forward transforms use the generic two-pass kernels,
-// the inverse ones the fast kernels when the plan has them; one region serves both
-static size_t tm_ring_bytes(const HostPlan& hp) {
+// the inverse ones the fast kernels when the plan has them; one region serves both (and the groups' sub-plans)
+static size_t tm_ring_bytes(const nwcwt_plan* pl) {
+    const HostPlan& hp = pl->hp;
     const size_t cs = cx_size(hp.dtype);
-    size_t b = (size_t)hp.ring * hp.tm_stride * cs;
+    size_t b = hp.generic_ok ? (size_t)hp.ring * hp.tm_stride * cs : 0;
     if (hp.fast) b = std::max<size_t>(b, (size_t)nwcwt_plan::MAX_AUX * (size_t)hp.ring2 * (size_t)hp.tm_stride2 * cs);
+    for (const nwcwt_plan::Group& g : pl->groups) b = std::max(b, tm_ring_bytes(g.sub));
     return align_up(b, 256);
+}
+// decimated rows of the resampled groups: per stream slot, the rows of one launch pair
+static size_t y_ring_bytes(const nwcwt_plan* pl) {
+    size_t b = 0;
+    for (size_t gi = 0; gi < pl->groups.size(); ++gi) {
+        const HostPlan& sh = pl->groups[gi].sub->hp;
+        if (pl->hp.groups[gi].D > 1) b = std::max(b, (size_t)sh.ring2 * (size_t)sh.N * cx_size(sh.dtype));
+    }
+    return align_up(b * nwcwt_plan::MAX_AUX, 256);
 }
 
 template <typename T>
-static Long2Params<T> make_long2(nwcwt_plan* pl) {
+static Long2Params<T> make_long2(const nwcwt_plan* pl) {
     const HostPlan& hp = pl->hp;
     Long2Params<T> P;
     memset(&P, 0, sizeof(P));
     P.N = hp.N;
+    P.xstride = hp.data_len();
     P.N1 = hp.N1f;
     P.N2 = hp.N2f;
     P.F = hp.F;
@@ -434,22 +466,102 @@ static Long2Params<T> make_long2(nwcwt_plan* pl) {
     P.twL = (const cx<T>*)pl->d_twL;
     P.lb = hp.lb;
     P.tm_stride = hp.tm_stride2;
-    P.pplans = (const PrunePlan*)pl->d_pplans;
     P.sp = make_spec<T>(pl);
+    if (hp.stA2.nst >= 1) P.dstepA = make_fastdiv((uint32_t)std::max(1, hp.N1f / hp.stA2.radix[hp.stA2.nst - 1]));
     return P;
 }
 
-// workspace layout of the long path: [ring] spectra of N, then the Tm ring
+// Inverse transforms of gs signals x the frequencies of plan `ep` on the packed kernels: ep is the plan itself
+// (every row, exact) or the sub-plan of one of its groups.  Rows go out in launch pairs of ep->ring2 rows that
+// alternate between the plan's auxiliary streams (forked from / joined into `stream` by the caller).
+//   grp == nullptr or D == 1: pass B writes the final output rows (through the group's frequency map)
+//   D > 1: pass B writes the decimated rows into the stream slot's Y buffer and the interpolation kernel
+//          (nw_resample.cuh) turns them into the output rows
+template <typename T>
+static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X, cx<T>* Tm, cx<T>* Y, void* out_s0, int gs,
+                        int output, cudaStream_t stream, int& launch_idx) {
+    const HostPlan& hp = pl->hp;
+    const HostPlan& eh = ep->hp;
+    const MrGroup* mg = gidx >= 0 ? &hp.groups[(size_t)gidx] : nullptr;
+    const nwcwt_plan::Group* dg = gidx >= 0 ? &pl->groups[(size_t)gidx] : nullptr;
+    const int D = mg ? mg->D : 1;
+    const size_t esz = (output == NWCWT_OUT_CWT) ? sizeof(cx<T>) : sizeof(T);
+    Long2Params<T> Q = make_long2<T>(ep);
+    Q.X = X;
+    Q.xstride = hp.N;
+    const unsigned tA = (unsigned)((eh.N2f + (2 << eh.tpshA) - 1) / (2 << eh.tpshA));
+    const unsigned tB = (unsigned)((eh.N1f + (2 << eh.tpshB) - 1) / (2 << eh.tpshB));
+    const long long rows = (long long)gs * eh.F;
+    const int ns = pl->n_aux;
+    // kernels specialised for this plan at compile time, where the library has them
+    int spA = g_no_static ? 0 : static_plan_id(eh.stA2, eh.tpshA), spB = g_no_static ? 0 : static_plan_id(eh.stB2, eh.tpshB);
+    if (!Long2Dispatch<T>::has(eh.cfgA, 0, spA)) spA = 0;
+    if (!Long2Dispatch<T>::has(eh.cfgB, 1, spB)) spB = 0;
+    ResampleParams<T> R;
+    ResampleShape shp{1, 1, 0, 0, 0};
+    if (D > 1) {
+        shp = resample_shape<T>(D, mg->K);
+        memset(&R, 0, sizeof(R));
+        R.ystride = eh.N;
+        R.out = out_s0;
+        R.N = hp.N;
+        R.M = (int)eh.N;
+        R.D = D;
+        R.coef = (const T*)dg->d_coef;
+        R.t0 = dg->d_t0;
+        R.t0min = dg->t0min;
+        R.fmap = dg->d_fmap;
+        R.F = eh.F;
+        R.F_out = hp.F;
+        R.WR = shp.WR;
+        R.WP = shp.WP;
+        R.RS = shp.RS;
+        R.dRD = make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
+        Q.eq = (const T*)dg->d_eq;
+        Q.out_mode = NWCWT_OUT_CWT;
+    } else {
+        Q.out = out_s0;
+        Q.out_mode = output;
+        if (dg) { Q.fmap = dg->d_fmap; Q.F_out = hp.F; }
+    }
+    for (long long r0 = 0; r0 < rows; r0 += eh.ring2, ++launch_idx) {
+        const int g = (int)std::min<long long>(eh.ring2, rows - r0);
+        const int slot = ns > 1 ? launch_idx % ns : 0;
+        cudaStream_t st = ns > 1 ? pl->aux[slot] : stream;
+        Q.row0 = (int)r0;
+        Q.Tm = Tm + (size_t)slot * (size_t)eh.ring2 * (size_t)eh.tm_stride2;
+        Q.narrow = group_narrow(eh, r0, g) ? 1 : 0;
+        cx<T>* yslot = nullptr;
+        if (D > 1) {
+            yslot = Y + (size_t)slot * (size_t)eh.ring2 * (size_t)eh.N;
+            Q.out = (char*)yslot - (size_t)r0 * (size_t)eh.N * sizeof(cx<T>);   // pass B indexes rows from row0
+        }
+        { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(eh.cfgA, spA, Q, dim3(tA, g), eh.nthrA2, eh.smem_A2, st)); }
+        { LaunchScope ls(4, st); CUDA_TRY(Long2Dispatch<T>::B(eh.cfgB, spB, Q, dim3(tB, g), eh.nthrB2, eh.smem_B2, st)); }
+        if (D > 1) {
+            R.y = yslot;
+            R.row0 = (int)r0;
+            const unsigned tiles = (unsigned)((eh.N + shp.C - 1) / shp.C);
+            LaunchScope ls(6, st);
+            CUDA_TRY(launch_resample<T>(mg->K, output, R, dim3(tiles, g), 32 * shp.WR * shp.WP, shp.smem, st));
+        }
+    }
+    (void)esz;
+    return 0;
+}
+
+// workspace layout of the long path: [ring] spectra of N, the Tm ring, the Y ring of the resampled groups
 template <typename T>
 static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spectra_out, long long S, int output,
                        int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
                        bool forward_only) {
     const HostPlan& hp = pl->hp;
     const size_t xbytes = align_up((size_t)hp.ring * hp.N * sizeof(cx<T>), 256);
-    const size_t tbytes = tm_ring_bytes(hp);
-    if (ws_bytes < xbytes + tbytes || !ws) return fail(NWCWT_ERR_WORKSPACE, "workspace too small");
+    const size_t tbytes = tm_ring_bytes(pl), ybytes = y_ring_bytes(pl);
+    if (ws_bytes < xbytes + tbytes + ybytes || !ws) return fail(NWCWT_ERR_WORKSPACE, "workspace too small");
     cx<T>* X = (cx<T>*)ws;
     cx<T>* Tm = (cx<T>*)((char*)ws + xbytes);
+    cx<T>* Y = (cx<T>*)((char*)ws + xbytes + tbytes);
     LongParams<T> P = make_long<T>(pl);
     P.Tm = Tm;
     const int TA = 1 << hp.tshA, TB = 1 << hp.tshB;
@@ -459,7 +571,7 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
         const int gs = (int)std::min<long long>(hp.ring, S - s0);
         // forward transforms of gs signals (scipy.fftpack.fft, base.py:399)
         cx<T>* Xdst = forward_only ? (cx<T>*)spectra_out + (size_t)s0 * hp.N : X;
-        if (hp.fast && !g_force_generic && !g_fwd_generic) {
+        if (hp.fast && !g_force_generic) {
             // packed kernels, conjugate transform; chunks of ring2 signals share the first Tm slot
             Long2Params<T> Qf = make_long2<T>(pl);
             Qf.Tm = Tm;
@@ -483,58 +595,22 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
         }
         if (forward_only) continue;
         if (hp.fast && !g_force_generic) {
-            // inverse transforms of all gs * F rows of the group, ring2 rows per launch pair
-            Long2Params<T> Q = make_long2<T>(pl);
-            Q.X = X;
-            Q.Tm = Tm;
-            Q.out = (char*)out + (size_t)s0 * hp.F * (size_t)hp.N * esz;
-            Q.out_mode = output;
-            const unsigned tA = (unsigned)((hp.N2f + (2 << hp.tpshA) - 1) / (2 << hp.tpshA));
-            const unsigned tB = (unsigned)((hp.N1f + (2 << hp.tpshB) - 1) / (2 << hp.tpshB));
-            const long long rows = (long long)gs * hp.F;
+            // inverse transforms of all gs * F rows of the signal group
+            void* out_s0 = (char*)out + (size_t)s0 * hp.F * (size_t)hp.N * esz;
             const int ns = pl->n_aux;
-            // kernels specialised for this plan at compile time, where the library has them
-            int spA = g_no_static ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = g_no_static ? 0 : static_plan_id(hp.stB2, hp.tpshB);
-            if (!Long2Dispatch<T>::has(hp.cfgA, 0, spA)) spA = 0;
-            if (hp.pruneA && pl->d_pplans) spA = -1;
-            if (!Long2Dispatch<T>::has(hp.cfgB, 1, spB)) spB = 0;
             if (ns > 1) {
                 CUDA_TRY(cudaEventRecord(pl->ev_fork, stream));
                 for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(pl->aux[i], pl->ev_fork, 0));
             }
-            // keep the Tm slots in use resident in L2 (hit -> persisting, everything else on these streams streams)
-            {
-                const size_t used = (size_t)std::max(ns, 1) * (size_t)hp.ring2 * (size_t)hp.tm_stride2 * sizeof(cx<T>);
-                if (pl->l2_persist_max && pl->l2_window_max && (pl->l2_window_base != (const void*)Tm || pl->l2_window_bytes != used)) {
-                    cudaStreamAttrValue av;
-                    memset(&av, 0, sizeof(av));
-                    av.accessPolicyWindow.base_ptr = (void*)Tm;
-                    av.accessPolicyWindow.num_bytes = std::min(used, pl->l2_window_max);
-                    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)pl->l2_persist_max / (double)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
-                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                    if (ns > 1) for (int i = 0; i < ns; ++i) cudaStreamSetAttribute(pl->aux[i], cudaStreamAttributeAccessPolicyWindow, &av);
-                    else cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
-                    pl->l2_window_base = (const void*)Tm;
-                    pl->l2_window_bytes = used;
-                }
+            int launch_idx = 0, rc = 0;
+            const bool resampled = !pl->groups.empty() && output != NWCWT_OUT_CWT && !g_exact;
+            if (resampled) {
+                for (size_t gi = 0; gi < pl->groups.size() && !rc; ++gi)
+                    rc = inverse_rows<T>(pl, pl->groups[gi].sub, (int)gi, X, Tm, Y, out_s0, gs, output, stream, launch_idx);
+            } else {
+                rc = inverse_rows<T>(pl, pl, -1, X, Tm, Y, out_s0, gs, output, stream, launch_idx);
             }
-            int gi = 0;
-            for (long long r0 = 0; r0 < rows; r0 += hp.ring2, ++gi) {
-                const int g = (int)std::min<long long>(hp.ring2, rows - r0);
-                const int slot = ns > 1 ? gi % ns : 0;
-                cudaStream_t st = ns > 1 ? pl->aux[slot] : stream;
-                Q.row0 = (int)r0;
-                Q.Tm = Tm + (size_t)slot * (size_t)hp.ring2 * (size_t)hp.tm_stride2;
-                Q.n_sm = device_sms(hp.device);
-                Q.tm_mod = g_tm_mod;
-                Q.narrow = group_narrow(hp, r0, g) ? 1 : 0;
-                if (hp.stA2.nst >= 1) Q.dstepA = make_fastdiv((uint32_t)std::max(1, hp.N1f / hp.stA2.radix[hp.stA2.nst - 1]));
-                Q.skew = g_skew_a; Q.skew_mod = g_skew_mod_a;
-                { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(hp.cfgA, spA, Q, dim3(tA, g), hp.nthrA2, hp.smem_A2, st)); }
-                Q.skew = g_skew_b; Q.skew_mod = g_skew_mod_b;
-                { LaunchScope ls(4, st); CUDA_TRY(Long2Dispatch<T>::B(hp.cfgB, spB, Q, dim3(tB, g), hp.nthrB2, hp.smem_B2, st)); }
-            }
+            if (rc) return rc;
             if (ns > 1)
                 for (int i = 0; i < ns; ++i) {
                     CUDA_TRY(cudaEventRecord(pl->ev_join[i], pl->aux[i]));
@@ -542,7 +618,7 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
                 }
             if (bl != NWCWT_BL_NONE) {
                 LaunchScope ls(5, stream);
-                nwcwt_baseline_rows_kernel<T><<<(unsigned)rows, 512, 0, stream>>>((T*)Q.out, hp.N, bl, (int)blo, (int)bhi);
+                nwcwt_baseline_rows_kernel<T><<<(unsigned)((long long)gs * hp.F), 512, 0, stream>>>((T*)out_s0, hp.N, bl, (int)blo, (int)bhi);
             }
             continue;
         }
@@ -605,12 +681,17 @@ int nwcwt_debug_force_generic(int32_t on) {
     return 0;
 }
 
+int nwcwt_debug_force_exact(int32_t on) {
+    g_exact = on != 0;
+    return 0;
+}
+
 int nwcwt_profile_enable(int32_t on) {
     g_profile = on != 0;
     return 0;
 }
 
-int nwcwt_profile_read(double ms[6], int64_t launches[6]) {
+int nwcwt_profile_read(double ms[8], int64_t launches[8]) {
     if (!ms || !launches) return fail(NWCWT_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (ProfEvent& e : g_prof_events) {
@@ -623,7 +704,7 @@ int nwcwt_profile_read(double ms[6], int64_t launches[6]) {
         cudaEventDestroy(e.b);
     }
     g_prof_events.clear();
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < N_PROF; ++i) {
         ms[i] = g_prof_ms[i];
         launches[i] = g_prof_n[i];
         g_prof_ms[i] = 0;
@@ -668,6 +749,8 @@ int nwcwt_plan_create(nwcwt_plan** out, const nwcwt_plan_desc* d) {
         hp.table.assign(d->table, d->table + 2 * (size_t)d->n_freqs * (size_t)d->table_len);
         if (d->table_lens) hp.table_lens.assign(d->table_lens, d->table_lens + d->n_freqs);
     }
+    hp.resample = d->resample >= 0 ? 1 : 0;
+    hp.resample_tol = d->resample_tol;
     plan_geometry(hp);
     plan_bands(hp);
     std::string err;
@@ -675,15 +758,31 @@ int nwcwt_plan_create(nwcwt_plan** out, const nwcwt_plan_desc* d) {
         delete pl;
         return fail(NWCWT_ERR_UNSUPPORTED, err);
     }
+    for (const MrGroup& mg : hp.groups) {
+        nwcwt_plan::Group g;
+        g.sub = new nwcwt_plan();
+        g.sub->hp = *mg.sub;
+        g.sub->is_sub = true;
+        pl->groups.push_back(g);
+    }
     *out = pl;
     return 0;
 }
 
 int nwcwt_plan_destroy(nwcwt_plan* pl) {
     if (!pl) return 0;
+    for (nwcwt_plan::Group& g : pl->groups) {
+        if (g.sub && g.sub->on_device) {
+            cudaSetDevice(pl->hp.device);
+            void* ptrs[] = {g.d_coef, g.d_eq, g.d_t0, g.d_fmap};
+            for (void* q : ptrs) if (q) cudaFree(q);
+        }
+        nwcwt_plan_destroy(g.sub);
+    }
+    pl->groups.clear();
     if (pl->on_device || pl->h_stream[0]) {
         cudaSetDevice(pl->hp.device);
-        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_twA2, pl->d_twB2, pl->d_pplans,
+        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_twA2, pl->d_twB2,
                         pl->h_in_dev[0], pl->h_in_dev[1], pl->h_out_dev[0], pl->h_out_dev[1], pl->h_ws[0], pl->h_ws[1]};
         for (void* p : ptrs)
             if (p) cudaFree(p);
@@ -707,6 +806,16 @@ int nwcwt_plan_get_info(const nwcwt_plan* pl, nwcwt_plan_info* info) {
     info->n_freqs = hp.F;
     info->path = hp.path;
     info->band_bins = hp.band_bins;
+    info->n_groups = (int32_t)std::min<size_t>(hp.groups.size(), 32);
+    for (int g = 0; g < info->n_groups; ++g) {
+        const MrGroup& mg = hp.groups[(size_t)g];
+        info->group_D[g] = mg.D;
+        info->group_K[g] = mg.K;
+        info->group_rows[g] = (int32_t)mg.fidx.size();
+        info->group_n1[g] = mg.sub->N1f;
+        info->group_n2[g] = mg.sub->N2f;
+        info->group_err[g] = mg.err;
+    }
     if (hp.path == 0) {
         info->batch = 1 << hp.tsh;
         info->n_stages[0] = hp.st.nst;
@@ -767,7 +876,7 @@ int nwcwt_workspace_bytes(const nwcwt_plan* pl, int64_t n_signals, size_t* bytes
         return 0;
     }
     const size_t cs = cx_size(hp.dtype);
-    *bytes = align_up((size_t)hp.ring * hp.N * cs, 256) + tm_ring_bytes(hp);
+    *bytes = align_up((size_t)hp.ring * hp.N * cs, 256) + tm_ring_bytes(pl) + y_ring_bytes(pl);
     return 0;
 }
 

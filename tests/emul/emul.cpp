@@ -16,6 +16,7 @@
 #include "../../ninwavelets_b200/csrc/nw_kernels.cuh"
 #include "../../ninwavelets_b200/csrc/nw_kernels2.cuh"
 #include "../../ninwavelets_b200/csrc/nw_kernels3.cuh"
+#include "../../ninwavelets_b200/csrc/nw_resample.cuh"
 #include "../../ninwavelets_b200/csrc/nw_plan.h"
 
 #include <ucontext.h>
@@ -80,19 +81,122 @@ static void fill_tw(std::vector<cx<T>>& v, long long count, long long P, long lo
     }
 }
 
+// SpecParams of a plan (the main one or a group's sub-plan)
+template <typename T>
+static SpecParams<T> make_sp(const HostPlan& hp, const std::vector<cx<T>>& table) {
+    SpecParams<T> sp;
+    sp.family = hp.family; sp.grid_off = hp.grid_off; sp.df = hp.df; sp.p0 = hp.p0; sp.p1 = hp.p1;
+    sp.p2 = hp.family == FAM_MORSE ? hp.p0 / hp.p1 : hp.p2;
+    sp.norm = (T)(1.0 / (double)hp.data_len());
+    sp.rec = hp.rec.data(); sp.table = table.data(); sp.table_len = hp.table_len;
+    return sp;
+}
+template <typename T>
+static void make_table(const HostPlan& hp, std::vector<cx<T>>& table) {
+    table.clear();
+    if (hp.family != FAM_TABLE) return;
+    table.resize((size_t)hp.F * hp.table_len);
+    for (size_t i = 0; i < table.size(); ++i) { table[i].x = (T)hp.table[2 * i]; table[i].y = (T)hp.table[2 * i + 1]; }
+}
+
+template <typename T, int K>
+static void resample_launch(const ResampleParams<T>& R, int mode, char* smp, int tiles, int g, int nt) {
+    for (int y = 0; y < g; ++y) for (int x = 0; x < tiles; ++x)
+        Fibers::get().run(nt, [&](int t) {
+            if (mode == OUT_POWER) resample_body<T, K, ResampleRun<T>::R, OUT_POWER>(R, smp, x, y, t, nt);
+            else resample_body<T, K, ResampleRun<T>::R, OUT_ABS>(R, smp, x, y, t, nt);
+        });
+}
+
+// Inverse transforms of gs signals x the frequencies of plan eh (the main plan, or the sub-plan of group mg) on the
+// packed kernels, followed by the interpolation kernel for a resampled group: mirrors nwcwt.cu: inverse_rows.
+template <typename T>
+static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* mg, const cx<T>* X, void* out_s0, int gs, int output) {
+    std::vector<cx<T>> table, twA2, twB2, twH, twL;
+    make_table<T>(eh, table);
+    fill_tw<T>(twA2, eh.N1f, eh.N1f, 1);
+    fill_tw<T>(twB2, eh.N2f, eh.N2f, 1);
+    const long long nL = 1LL << eh.lb, nH = (eh.N + nL - 1) / nL;
+    fill_tw<T>(twL, nL, eh.N, 1);
+    fill_tw<T>(twH, nH, eh.N, nL);
+    const int D = mg ? mg->D : 1;
+    Long2Params<T> Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.N = eh.N; Q.xstride = hp.N; Q.N1 = eh.N1f; Q.N2 = eh.N2f; Q.F = eh.F; Q.tpshA = eh.tpshA; Q.tpshB = eh.tpshB;
+    Q.stA = eh.stA2; Q.stB = eh.stB2; Q.twA = twA2.data(); Q.twB = twB2.data(); Q.twH = twH.data(); Q.twL = twL.data();
+    Q.lb = eh.lb; Q.tm_stride = eh.tm_stride2; Q.sp = make_sp<T>(eh, table);
+    const int ring2 = eh.ring2 < 3 ? eh.ring2 : 3;
+    std::vector<cx<T>> Tm2((size_t)ring2 * eh.tm_stride2), Y;
+    Q.X = X; Q.Tm = Tm2.data();
+    std::vector<T> eq, coef;
+    ResampleParams<T> R;
+    ResampleShape shp{1, 1, 0, 0, 0};
+    memset(&R, 0, sizeof(R));
+    if (D > 1) {
+        eq.assign(mg->eq.begin(), mg->eq.end());
+        coef.assign(mg->coef.begin(), mg->coef.end());
+        Y.resize((size_t)ring2 * eh.N);
+        shp = resample_shape<T>(D, mg->K);
+        R.ystride = eh.N; R.out = out_s0; R.N = hp.N; R.M = (int)eh.N; R.D = D; R.coef = coef.data(); R.t0 = mg->t0.data();
+        R.t0min = *std::min_element(mg->t0.begin(), mg->t0.end());
+        R.fmap = mg->fidx.data(); R.F = eh.F; R.F_out = hp.F; R.WR = shp.WR; R.WP = shp.WP; R.RS = shp.RS;
+        R.dRD = make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
+        Q.eq = eq.data();
+        Q.out_mode = OUT_CWT;
+    } else {
+        Q.out = out_s0; Q.out_mode = output;
+        if (mg) { Q.fmap = mg->fidx.data(); Q.F_out = hp.F; }
+    }
+    const int tA = (eh.N2f + (2 << eh.tpshA) - 1) / (2 << eh.tpshA), tB = (eh.N1f + (2 << eh.tpshB) - 1) / (2 << eh.tpshB);
+    std::vector<char> sm2(std::max(std::max(eh.smem_A2, eh.smem_B2), shp.smem) + 64);
+    char* smp = (char*)(((uintptr_t)sm2.data() + 31) & ~(uintptr_t)31);
+    const int ntA = (g_mode & 4) ? 1 : eh.nthrA2, ntB = (g_mode & 4) ? 1 : eh.nthrB2;
+    const long long rows = (long long)gs * eh.F;
+    if (eh.stA2.nst >= 1) Q.dstepA = make_fastdiv((uint32_t)std::max(1, eh.N1f / eh.stA2.radix[eh.stA2.nst - 1]));
+    const int spA = (g_mode & 8) ? 0 : static_plan_id(eh.stA2, eh.tpshA), spB = (g_mode & 8) ? 0 : static_plan_id(eh.stB2, eh.tpshB);
+    const int omode = D > 1 ? OUT_CWT : output;
+    for (long long r0 = 0; r0 < rows; r0 += ring2) {
+        const int g = (int)std::min<long long>(ring2, rows - r0);
+        Q.row0 = (int)r0;
+        if (D > 1) Q.out = (char*)Y.data() - (size_t)r0 * (size_t)eh.N * sizeof(cx<T>);
+        for (int y = 0; y < g; ++y) for (int x = 0; x < tA; ++x)
+            Fibers::get().run(ntA, [&](int t) {
+                if (group_narrow(eh, r0, g) && !(g_mode & 64)) {
+                    if (spA == 2) passA2_body<T, 2, true>(Q, smp, x, y, t, ntA);
+                    else passA2_body<T, 0, true>(Q, smp, x, y, t, ntA);
+                } else {
+                    if (spA == 2) passA2_body<T, 2>(Q, smp, x, y, t, ntA);
+                    else if (spA == 4) passA2_body<T, 4>(Q, smp, x, y, t, ntA);
+                    else passA2_body<T, 0>(Q, smp, x, y, t, ntA);
+                }
+            });
+        for (int y = 0; y < g; ++y) for (int x = 0; x < tB; ++x)
+            Fibers::get().run(ntB, [&](int t) {
+                if (omode == OUT_POWER) { if (spB == 1) passB2_body<T, OUT_POWER, 1>(Q, smp, x, y, t, ntB); else if (spB == 4) passB2_body<T, OUT_POWER, 4>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_POWER, 0>(Q, smp, x, y, t, ntB); }
+                else if (omode == OUT_ABS) passB2_body<T, OUT_ABS, 0>(Q, smp, x, y, t, ntB);
+                else { if (spB == 1) passB2_body<T, OUT_CWT, 1>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_CWT, 0>(Q, smp, x, y, t, ntB); }
+            });
+        if (D > 1) {
+            R.y = Y.data(); R.row0 = (int)r0;
+            const int tiles = (int)((eh.N + shp.C - 1) / shp.C), nt = 32 * shp.WR * shp.WP;
+            switch (mg->K) {
+#define RS_CASE(k) case k: resample_launch<T, k>(R, output, smp, tiles, g, nt); break;
+                RS_CASE(4) RS_CASE(5) RS_CASE(6) RS_CASE(7) RS_CASE(8) RS_CASE(9) RS_CASE(10) RS_CASE(11) RS_CASE(12) RS_CASE(13)
+                RS_CASE(14) RS_CASE(15) RS_CASE(16) RS_CASE(18) RS_CASE(20) RS_CASE(22) RS_CASE(24)
+#undef RS_CASE
+                default: return -2;
+            }
+        }
+    }
+    return 0;
+}
+
 template <typename T>
 static int run(const HostPlan& hp, const void* signals, void* out, long long S, int output, int bl, long long blo,
                long long bhi) {
     std::vector<cx<T>> table;
-    if (hp.family == FAM_TABLE) {
-        table.resize((size_t)hp.F * hp.table_len);
-        for (size_t i = 0; i < table.size(); ++i) { table[i].x = (T)hp.table[2 * i]; table[i].y = (T)hp.table[2 * i + 1]; }
-    }
-    SpecParams<T> sp;
-    sp.family = hp.family; sp.grid_off = hp.grid_off; sp.df = hp.df; sp.p0 = hp.p0; sp.p1 = hp.p1;
-    sp.p2 = hp.family == FAM_MORSE ? hp.p0 / hp.p1 : hp.p2;
-    sp.norm = (T)(1.0 / (double)hp.N);
-    sp.rec = hp.rec.data(); sp.table = table.data(); sp.table_len = hp.table_len;
+    make_table<T>(hp, table);
+    SpecParams<T> sp = make_sp<T>(hp, table);
     const size_t esz = output == OUT_CWT ? sizeof(cx<T>) : sizeof(T);
     if (hp.path == 0 && hp.short2 && !(g_mode & 2)) {
         std::vector<cx<T>> tw;
@@ -157,7 +261,7 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
             fill_tw<T>(twB2, hp.N2f, hp.N2f, 1);
             Long2Params<T> Q;
             memset(&Q, 0, sizeof(Q));
-            Q.N = hp.N; Q.N1 = hp.N1f; Q.N2 = hp.N2f; Q.F = hp.F; Q.tpshA = hp.tpshA; Q.tpshB = hp.tpshB;
+            Q.N = hp.N; Q.xstride = hp.N; Q.N1 = hp.N1f; Q.N2 = hp.N2f; Q.F = hp.F; Q.tpshA = hp.tpshA; Q.tpshB = hp.tpshB;
             Q.stA = hp.stA2; Q.stB = hp.stB2; Q.twA = twA2.data(); Q.twB = twB2.data(); Q.twH = twH.data(); Q.twL = twL.data();
             Q.lb = hp.lb; Q.tm_stride = hp.tm_stride2; Q.out_mode = OUT_CWT;
             std::vector<cx<T>> Tmf((size_t)hp.tm_stride2);
@@ -180,52 +284,16 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
         for (int y = 0; y < gs; ++y) for (int x = 0; x < tilesB; ++x) passB_body<T, -1>(P, smem.data(), x, y, 0, 1);
         }
         if (hp.fast && !(g_mode & 2)) {
-            std::vector<cx<T>> twA2, twB2;
-            fill_tw<T>(twA2, hp.N1f, hp.N1f, 1);
-            fill_tw<T>(twB2, hp.N2f, hp.N2f, 1);
-            Long2Params<T> Q;
-            memset(&Q, 0, sizeof(Q));
-            Q.N = hp.N; Q.N1 = hp.N1f; Q.N2 = hp.N2f; Q.F = hp.F; Q.tpshA = hp.tpshA; Q.tpshB = hp.tpshB;
-            Q.stA = hp.stA2; Q.stB = hp.stB2; Q.twA = twA2.data(); Q.twB = twB2.data(); Q.twH = twH.data(); Q.twL = twL.data();
-            Q.lb = hp.lb; Q.tm_stride = hp.tm_stride2; Q.sp = sp;
-            const int ring2 = hp.ring2 < 3 ? hp.ring2 : 3;
-            std::vector<cx<T>> Tm2((size_t)ring2 * hp.tm_stride2);
-            Q.X = X.data(); Q.Tm = Tm2.data();
-            Q.out = (char*)out + (size_t)s0 * hp.F * (size_t)hp.N * esz; Q.out_mode = output;
-            const int tA = (hp.N2f + (2 << hp.tpshA) - 1) / (2 << hp.tpshA), tB = (hp.N1f + (2 << hp.tpshB) - 1) / (2 << hp.tpshB);
-            std::vector<char> sm2(std::max(hp.smem_A2, hp.smem_B2) + 64);
-            char* smp = (char*)(((uintptr_t)sm2.data() + 31) & ~(uintptr_t)31);
-            const int ntA = (g_mode & 4) ? 1 : hp.nthrA2, ntB = (g_mode & 4) ? 1 : hp.nthrB2;
+            void* out_s0 = (char*)out + (size_t)s0 * hp.F * (size_t)hp.N * esz;
             const long long rows = (long long)gs * hp.F;
-            Q.pplans = hp.pplans.data();
-            if (hp.stA2.nst >= 1) Q.dstepA = make_fastdiv((uint32_t)std::max(1, hp.N1f / hp.stA2.radix[hp.stA2.nst - 1]));
-            const int spA = (hp.pruneA && !(g_mode & 16)) ? -1 : (g_mode & 8) ? 0 : static_plan_id(hp.stA2, hp.tpshA), spB = (g_mode & 8) ? 0 : static_plan_id(hp.stB2, hp.tpshB);
-            for (long long r0 = 0; r0 < rows; r0 += ring2) {
-                const int g = (int)std::min<long long>(ring2, rows - r0);
-                Q.row0 = (int)r0;
-                for (int y = 0; y < g; ++y) for (int x = 0; x < tA; ++x)
-                    Fibers::get().run(ntA, [&](int t) {
-                        if (spA == -1) passA2p_body<T>(Q, smp, x, y, t, ntA);
-                        else if (group_narrow(hp, r0, g) && !(g_mode & 64)) {
-                            if (spA == 2) passA2_body<T, 2, true>(Q, smp, x, y, t, ntA);
-                            else passA2_body<T, 0, true>(Q, smp, x, y, t, ntA);
-                        } else {
-                            if (spA == 2) passA2_body<T, 2>(Q, smp, x, y, t, ntA);
-                            else if (spA == 4) passA2_body<T, 4>(Q, smp, x, y, t, ntA);
-                            else if (spA == 11) passA2_body<T, 11>(Q, smp, x, y, t, ntA);
-                            else passA2_body<T, 0>(Q, smp, x, y, t, ntA);
-                        }
-                    });
-                for (int y = 0; y < g; ++y) for (int x = 0; x < tB; ++x)
-                    Fibers::get().run(ntB, [&](int t) {
-                        if (output == OUT_POWER) { if (spB == 1) passB2_body<T, OUT_POWER, 1>(Q, smp, x, y, t, ntB); else if (spB == 4) passB2_body<T, OUT_POWER, 4>(Q, smp, x, y, t, ntB); else if (spB == 8) passB2_body<T, OUT_POWER, 8>(Q, smp, x, y, t, ntB); else if (spB == 9) passB2_body<T, OUT_POWER, 9>(Q, smp, x, y, t, ntB); else if (spB == 10) passB2_body<T, OUT_POWER, 10>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_POWER, 0>(Q, smp, x, y, t, ntB); }
-                        else if (output == OUT_ABS) passB2_body<T, OUT_ABS, 0>(Q, smp, x, y, t, ntB);
-                        else { if (spB == 1) passB2_body<T, OUT_CWT, 1>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_CWT, 0>(Q, smp, x, y, t, ntB); }
-                    });
-            }
+            int rc = 0;
+            if (!hp.groups.empty() && output != OUT_CWT && !(g_mode & 128)) {
+                for (const MrGroup& mg : hp.groups)
+                    if ((rc = inverse_rows<T>(hp, *mg.sub, &mg, X.data(), out_s0, gs, output))) return rc;
+            } else if ((rc = inverse_rows<T>(hp, hp, nullptr, X.data(), out_s0, gs, output))) return rc;
             if (bl != BL_NONE) {
                 double sh[2];
-                for (long long r = 0; r < rows; ++r) baseline_rows_body<T>((T*)Q.out, hp.N, bl, (int)blo, (int)bhi, sh, (int)r, 0, 1);
+                for (long long r = 0; r < rows; ++r) baseline_rows_body<T>((T*)out_s0, hp.N, bl, (int)blo, (int)bhi, sh, (int)r, 0, 1);
             }
             continue;
         }
@@ -253,6 +321,8 @@ extern "C" int emul_transform(const nwcwt_plan_desc* d, const void* signals, voi
     hp.device = 0; hp.dtype = d->dtype; hp.family = d->family; hp.interpolate = d->interpolate ? 1 : 0;
     hp.N = d->n; hp.F = d->n_freqs; hp.sfreq = d->sfreq; hp.p0 = d->p0; hp.p1 = d->p1; hp.p2 = d->p2;
     hp.prune_eps = d->prune_eps < 0 ? (d->dtype == 0 ? 1e-12 : 1e-24) : d->prune_eps;
+    hp.resample = d->resample >= 0 ? 1 : 0;
+    hp.resample_tol = d->resample_tol;
     hp.freqs.assign(d->freqs, d->freqs + d->n_freqs);
     if (d->family == FAM_MORLET) hp.aux.assign(d->aux, d->aux + d->n_freqs);
     if (d->family == FAM_TABLE) {
@@ -264,7 +334,6 @@ extern "C" int emul_transform(const nwcwt_plan_desc* d, const void* signals, voi
     plan_bands(hp);
     std::string err;
     g_mode = force_long;
-    setenv("NWCWT_PRUNE", (force_long & 16) ? "0" : "1", 1);   // the emulation exercises the pruned pass A by default
     if (!plan_shape(hp, err, (force_long & 1) != 0)) {
         strncpy(errbuf, err.c_str(), errlen - 1);
         return -2;

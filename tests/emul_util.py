@@ -19,7 +19,7 @@ def _build():
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "nwcwt.h")]
     if os.path.isfile(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DNW_BIG_RADIX=1", "-fPIC", "-shared", "-o", LIB, SRC])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB, SRC])
 
 
 _lib = None
@@ -61,6 +61,8 @@ def emul_transform(fam_desc, signals, output, baseline=0, lo=0, hi=0, force_long
             keep.append(tl)
             d.table_lens = tl.ctypes.data_as(C.POINTER(C.c_int64))
     d.prune_eps = float(fam_desc.get("prune_eps", -1.0))
+    d.resample = int(fam_desc.get("resample", 0))
+    d.resample_tol = float(fam_desc.get("resample_tol", 0.0))
     F = len(freqs)
     odt = (np.complex128 if dtype == 1 else np.complex64) if output == 0 else rdt
     out = np.zeros((S, F, N), dtype=odt)
