@@ -36,4 +36,10 @@ template <typename T> cudaError_t prepare_resample();
 template <typename T> bool has_resample(int K);
 template <typename T>
 cudaError_t launch_resample(int K, int mode, const ResampleParams<T>& P, dim3 grid, int nthr, size_t smem, cudaStream_t s);
+// vector interpolation kernel (nw_resample.cuh: resample_vec_body): even K, PQ outputs per access, run length R
+static const int RSV_THREADS = 128;
+template <typename T, int PQ, int MODE> cudaError_t prepare_resample_vec();
+template <typename T, int PQ, int MODE> bool has_resample_vec(int K);
+template <typename T, int PQ, int MODE>
+cudaError_t launch_resample_vec(int K, int R, const ResampleParams<T>& P, dim3 grid, size_t smem, cudaStream_t s);
 }  // namespace nw

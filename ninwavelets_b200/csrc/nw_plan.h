@@ -689,56 +689,132 @@ inline void kb_response(int D, int K, double beta, long long M, const std::vecto
     }
 }
 
-// worst-case relative error of the K-tap kernel for a band of half width jmax (bins) at decimation D of N = M D
-inline double kb_worst_error(int D, int K, double beta, long long M, long long jmax) {
-    if (D < 2) return 0.0;
+// ---- error model ---------------------------------------------------------------------------------------------
+// A component of a row at transform bin j (offset from the band centre) reaches the output with its images at
+// j + r M, r = 1 .. D - 1, attenuated by H(j + r M) / H(j).  The planner bounds, for every row,
+//     max_j  |W_f(j)| / max|W_f|  *  sqrt(sum_r H(j + r M)^2) / |H(j)|   <=  resample_tol:
+// for ANY input, the interpolation error of the row is at most resample_tol times (largest spectrum value of the row's
+// wavelet) x (sum of the input's spectral magnitudes) - the scale the rounding error of the exact fp32 / fp64 transform
+// itself lives on.  Bins whose weight is below resample_tol / 8 are dropped from a resampled row's band.
+
+// alias gain A(j) of the kernel (D, K, beta) at NA + 1 offsets j = i * (M / 2) / NA
+static const int KB_NA = 64;
+inline void kb_alias_curve(int D, int K, double beta, long long M, std::vector<double>& A) {
     std::vector<long long> bins;
-    const int NP = 9;   // the error grows towards the band edge; sample the outer fifth and the centre
-    std::vector<long long> js;
-    for (int i = 0; i < NP; ++i) js.push_back(jmax - (long long)((double)jmax * 0.2 * (double)i / (double)(NP - 1)));
-    js.push_back(0);
-    for (long long j : js)
+    bins.reserve((size_t)(KB_NA + 1) * D);
+    for (int i = 0; i <= KB_NA; ++i) {
+        const long long j = (long long)((double)(M / 2) * (double)i / (double)KB_NA);
         for (int r = 0; r < D; ++r) bins.push_back(j + (long long)r * M);
+    }
     std::vector<double> H;
     kb_response(D, K, beta, M, bins, H);
-    double worst = 0.0;
-    for (size_t a = 0; a < js.size(); ++a) {
+    A.resize(KB_NA + 1);
+    for (int i = 0; i <= KB_NA; ++i) {
         double al = 0.0;
-        for (int r = 1; r < D; ++r) al += H[a * D + r] * H[a * D + r];
-        const double main = fabs(H[a * D]);
-        worst = std::max(worst, main > 0 ? sqrt(al) / main : 1e300);
+        for (int r = 1; r < D; ++r) al += H[(size_t)i * D + r] * H[(size_t)i * D + r];
+        const double main = fabs(H[(size_t)i * D]);
+        A[(size_t)i] = main > 0 ? sqrt(al) / main : 1e300;
     }
-    return worst;
+}
+// upper envelope of A on the cell that holds offset |j| (A is smooth on the scale of a cell; ripples span many cells)
+inline double kb_alias_at(const std::vector<double>& A, long long M, long long j) {
+    if (j < 0) j = -j;
+    const double u = (double)j / (double)(M / 2) * (double)KB_NA;
+    if (!(u < (double)KB_NA)) return 1e300;   // at or beyond M / 2: the image is as close as the component itself
+    const int i = (int)u;
+    return std::max(A[(size_t)i], A[(size_t)i + 1]);
 }
 
-// smallest K (and its beta) whose worst-case error is <= tol; false if none up to kmax
-inline bool kb_design(int D, long long M, long long jmax, double tol, int kmax, bool even, int& K, double& beta, double& err) {
-    const double os = (double)M / (2.0 * (double)std::max<long long>(jmax, 1));
-    if (os <= 1.02) return false;
-    const double PI = 3.14159265358979323846;
-    // estimate: error ~ 2 y exp(-y), y = pi K sqrt(1 - 1/os)  (about 3x pessimistic)
-    int k0 = 4;
-    for (; k0 < kmax; ++k0) {
-        const double y = PI * k0 * sqrt(1.0 - 1.0 / os);
-        if (2.0 * y * exp(-y) <= 4.0 * tol) break;
+// magnitude (any positive scale per frequency) of frequency fi's spectrum at data bin k
+inline double spec_mag_host(const HostPlan& hp, int fi, long long k) {
+    if (hp.family == FAM_TABLE) {
+        const long long m = hp.table_lens.empty() ? hp.table_len : hp.table_lens[(size_t)fi];
+        const long long idx = k - hp.rec[(size_t)fi].toff;
+        if (idx < 0 || idx >= m) return 0.0;
+        const double* t = &hp.table[2 * ((size_t)fi * (size_t)hp.table_len + (size_t)idx)];
+        return hypot(t[0], t[1]);
     }
-    for (int k = std::max(even ? 8 : 4, k0 - 2); k <= kmax; ++k) {
-        if (even && (k & 1)) continue;   // the fp64 kernels are compiled for even tap counts
-        double best = 1e300, bb = 0;
-        for (double f = 0.94; f <= 1.005; f += 0.02) {
-            const double b = f * PI * k * (1.0 - 0.5 / os);
-            const double e = kb_worst_error(D, k, b, M, jmax);
-            if (e < best) { best = e; bb = b; }
+    const double g = (double)(k - hp.grid_off) * hp.df, f = hp.freqs[(size_t)fi];
+    if (hp.family == FAM_MORSE) {
+        const double x = g / f;
+        return x > 0 ? exp(morse_logw(x, hp.p0, hp.p1)) : 0.0;
+    }
+    if (hp.family == FAM_MORLET) {
+        const double x = g / f * hp.aux[(size_t)fi], d = hp.p0 - x;
+        return fabs(exp(-0.5 * d * d) - hp.p2 * exp(-0.5 * x * x));
+    }
+    return 1.0;   // Shannon: flat inside the band
+}
+
+// Weight profile of one row: cells [pos[s], pos[s + 1]) of its band with an upper bound w[s] of |W| / max|W| on the cell,
+// and the resample band [rlo, rhi) outside of which the weight is below eps_rs.
+struct RowProfile {
+    std::vector<long long> pos;
+    std::vector<double> w;
+    long long rlo = 0, rhi = 0;
+};
+inline void row_profile(const HostPlan& hp, int fi, double eps_rs, RowProfile& rp) {
+    const FreqRec& r = hp.rec[(size_t)fi];
+    const long long lo = r.lo, hi = r.hi, B = hi - lo;
+    rp.pos.clear(); rp.w.clear();
+    rp.rlo = rp.rhi = lo;
+    if (B <= 0) return;
+    const int NS = (int)std::min<long long>(B, 384);
+    std::vector<double> mag((size_t)NS + 1);
+    rp.pos.resize((size_t)NS + 1);
+    for (int s = 0; s <= NS; ++s) rp.pos[(size_t)s] = lo + (long long)((double)B * (double)s / (double)NS);
+    rp.pos[(size_t)NS] = hi;
+    rp.w.assign((size_t)NS, 0.0);
+    double peak = 0.0;
+    if (hp.family == FAM_TABLE) {   // arbitrary shape: true maximum of every cell
+        for (int s = 0; s < NS; ++s) {
+            double m = 0.0;
+            for (long long k = rp.pos[(size_t)s]; k < rp.pos[(size_t)s + 1]; ++k) m = std::max(m, spec_mag_host(hp, fi, k));
+            rp.w[(size_t)s] = m;
+            peak = std::max(peak, m);
         }
-        if (best <= tol) { K = k; beta = bb; err = best; return true; }
+    } else {                        // smooth, single-peaked (Morlet: two-term) spectra: cell ends, the maximum refined by bisection
+        for (int s = 0; s <= NS; ++s) mag[(size_t)s] = spec_mag_host(hp, fi, std::min(rp.pos[(size_t)s], hi - 1));
+        int sm = 0;
+        for (int s = 0; s <= NS; ++s) if (mag[(size_t)s] > mag[(size_t)sm]) sm = s;
+        long long a = rp.pos[(size_t)std::max(0, sm - 1)], c = std::min(hi - 1, rp.pos[(size_t)std::min(NS, sm + 1)]);
+        peak = mag[(size_t)sm];
+        while (c - a > 2) {   // ternary search on the unimodal piece
+            const long long m1 = a + (c - a) / 3, m2 = c - (c - a) / 3;
+            const double v1 = spec_mag_host(hp, fi, m1), v2 = spec_mag_host(hp, fi, m2);
+            peak = std::max(peak, std::max(v1, v2));
+            if (v1 < v2) a = m1; else c = m2;
+        }
+        for (int s = 0; s < NS; ++s) rp.w[(size_t)s] = std::max(mag[(size_t)s], mag[(size_t)s + 1]);
+        for (int s = std::max(0, sm - 1); s < std::min(NS, sm + 1); ++s) rp.w[(size_t)s] = peak;
     }
-    return false;
+    if (!(peak > 0.0)) { rp.pos.clear(); rp.w.clear(); return; }
+    for (double& v : rp.w) v /= peak;
+    int s0 = 0, s1 = NS;
+    while (s0 < s1 && rp.w[(size_t)s0] < eps_rs) ++s0;
+    while (s1 > s0 && rp.w[(size_t)s1 - 1] < eps_rs) --s1;
+    rp.rlo = rp.pos[(size_t)s0];
+    rp.rhi = rp.pos[(size_t)s1];
+}
+// weighted worst-case error of a row for the alias curve A of a kernel at decimated length M; the row's band is centred
+inline double row_error(const RowProfile& rp, const std::vector<double>& A, long long M) {
+    const long long kc = rp.rlo + (rp.rhi - rp.rlo) / 2;
+    double e = 0.0;
+    for (size_t s = 0; s + 1 < rp.pos.size(); ++s) {
+        if (rp.pos[s + 1] <= rp.rlo || rp.pos[s] >= rp.rhi) continue;
+        const long long j0 = rp.pos[s] - kc, j1 = rp.pos[s + 1] - 1 - kc;
+        const long long j = std::max(j0 < 0 ? -j0 : j0, j1 < 0 ? -j1 : j1);
+        e = std::max(e, rp.w[s] * kb_alias_at(A, M, j));
+    }
+    return e;
 }
 
 inline void plan_shape_fast(HostPlan& hp);
 
-// Build the plan of a frequency subset at length M = N / D (D == 1: the exact transform of that subset).
-inline std::shared_ptr<HostPlan> make_sub_plan(const HostPlan& hp, const std::vector<int>& fidx, int D) {
+// Build the plan of a frequency subset at length M = N / D (D == 1: the exact transform of that subset).  bands: for
+// D > 1 the resample band [lo, hi) in data bins of every row of the subset.
+inline std::shared_ptr<HostPlan> make_sub_plan(const HostPlan& hp, const std::vector<int>& fidx, int D,
+                                               const std::vector<std::pair<long long, long long>>& bands) {
     std::shared_ptr<HostPlan> sp = std::make_shared<HostPlan>();
     HostPlan& s = *sp;
     s.device = hp.device; s.dtype = hp.dtype; s.family = hp.family; s.interpolate = hp.interpolate;
@@ -761,13 +837,19 @@ inline std::shared_ptr<HostPlan> make_sub_plan(const HostPlan& hp, const std::ve
     }
     plan_geometry(s);
     plan_bands(s);
-    if (D > 1)
-        for (FreqRec& r : s.rec) {   // centre the band on transform bin 0
+    if (D > 1) {
+        s.band_bins = 0;
+        for (size_t q = 0; q < s.rec.size(); ++q) {   // the resample band, centred on transform bin 0
+            FreqRec& r = s.rec[q];
+            r.lo = (int)std::max<long long>(r.lo, bands[q].first);
+            r.hi = (int)std::max<long long>(r.lo, std::min<long long>(r.hi, bands[q].second));
+            s.band_bins += r.hi - r.lo;
             const int kc = r.lo + (r.hi - r.lo) / 2;
             r.shift = kc;
             r.lo -= kc;
             r.hi -= kc;
         }
+    }
     s.path = 1;
     s.lb = (ilog2_floor(s.N) + 2) / 2;
     s.generic_ok = 0;
@@ -777,65 +859,94 @@ inline std::shared_ptr<HostPlan> make_sub_plan(const HostPlan& hp, const std::ve
     return sp;
 }
 
-// cost model, picoseconds per OUTPUT sample on B200 (profiles/r02: measured engine rate and interpolation kernel)
-struct MrCost { double engine, fir0, fir_tap; };
-inline MrCost mr_cost(int dtype) { return dtype == 0 ? MrCost{5.8, 0.8, 0.09} : MrCost{17.0, 1.6, 0.3}; }
+// cost model, picoseconds per OUTPUT sample on B200 (profiles/r02): engine = the packed two-pass transform per point of
+// its own length; interpolation = fir0 + fir_tap K with the vector kernel (even D), firs0 + firs_tap K with the scalar one
+struct MrCost { double engine, fir0, fir_tap, firs0, firs_tap; };
+inline MrCost mr_cost(int dtype) {
+    return dtype == 0 ? MrCost{8.0, 0.55, 0.035, 1.0, 0.18} : MrCost{20.0, 1.6, 0.3, 1.6, 0.3};
+}
+// the interpolation kernels a decimation can use: vector kernel (nw_resample.cuh: resample_vec_body) for even D in fp32
+inline bool resample_is_vec(int dtype, int D) { return dtype == 0 && (D & 1) == 0; }
 
 inline void plan_multirate(HostPlan& hp) {
     hp.groups.clear();
     if (hp.path != 1 || !hp.fast || hp.F <= 0 || hp.resample == 0 || hp.Nd > 0) return;
     if (env_int("NWCWT_NO_RESAMPLE", 0)) return;
     const long long N = hp.N;
-    const double tol = hp.resample_tol > 0 ? hp.resample_tol : (hp.dtype == 0 ? 5e-7 : 5e-14);
-    const int kmax = hp.dtype == 0 ? 16 : 24;   // tap counts the kernels are compiled for: 4..16 (fp32), 8, 10 .. 24 (fp64)
+    const double tol = hp.resample_tol > 0 ? hp.resample_tol : (hp.dtype == 0 ? 1e-6 : 5e-14);
+    const double eps_rs = tol / 8;
+    // tap counts the kernels are compiled for (even): 4 .. 12 (fp32 vector kernel), 4 .. 16 (fp32 scalar), 8 .. 24 (fp64)
+    const int kmin = hp.dtype == 0 ? 4 : 8, kmax_vec = 12, kmax = hp.dtype == 0 ? 16 : 24;
     // shortest decimated length: below it the engine's tiles are too small to pay (tests lower it to reach the path on
     // lengths the host emulation can afford)
     long long MMIN = env_int("NWCWT_RESAMPLE_MMIN", 16384);
     if (MMIN < 64) MMIN = 64;
     const MrCost cm = mr_cost(hp.dtype);
     // candidate decimations: divisors D of N with a fast plan at N / D
-    struct Cand { int D; long long M; };
-    std::vector<Cand> cands;
+    std::vector<int> cands;
     for (int D = 2; D <= 64; ++D) {
         if (N % D || N / D < MMIN) continue;
         HostPlan t;
         t.dtype = hp.dtype; t.N = N / D; t.F = 1;
         plan_shape_fast(t);
-        if (t.fast) cands.push_back(Cand{D, N / D});
+        if (t.fast) cands.push_back(D);
     }
     if (cands.empty()) return;
+    std::vector<RowProfile> prof((size_t)hp.F);
+    for (int i = 0; i < hp.F; ++i) row_profile(hp, i, eps_rs, prof[(size_t)i]);
+    // alias curves per (D, K, beta), built on demand; beta = fb pi K on a grid of fb
+    static const int NB = 9;
+    auto fb_of = [](int b) { return 0.52 + 0.06 * b; };
+    const double PI = 3.14159265358979323846;
+    struct Curve { bool have = false; std::vector<double> A; };
+    std::vector<Curve> curves(65 * 13 * NB);
+    auto curve = [&](int D, int K, int b) -> const std::vector<double>& {
+        Curve& c = curves[((size_t)D * 13 + (size_t)(K / 2)) * NB + (size_t)b];
+        if (!c.have) { kb_alias_curve(D, K, fb_of(b) * PI * K, N / D, c.A); c.have = true; }
+        return c.A;
+    };
+    // smallest even K (and its best beta) for which every listed row meets the tolerance at decimation D
+    auto design = [&](int D, const std::vector<int>& rows, int& K, int& bsel, double& err) -> bool {
+        const long long M = N / D;
+        const int kcap = resample_is_vec(hp.dtype, D) ? std::max(kmax_vec, kmin) : kmax;
+        for (int k = kmin; k <= kcap; k += 2) {
+            double best = 1e300;
+            int bb = 0;
+            for (int b = 0; b < NB; ++b) {
+                const std::vector<double>& A = curve(D, k, b);
+                double e = 0.0;
+                for (int i : rows) {
+                    e = std::max(e, row_error(prof[(size_t)i], A, M));
+                    if (e > best) break;
+                }
+                if (e < best) { best = e; bb = b; }
+            }
+            if (best <= tol) { K = k; bsel = bb; err = best; return true; }
+        }
+        return false;
+    };
     // per frequency: the cheapest decimation whose kernel meets the tolerance
     std::vector<int> pickD((size_t)hp.F, 1);
-    struct Key { int D; long long jmax; };
     for (int i = 0; i < hp.F; ++i) {
-        const FreqRec& r = hp.rec[(size_t)i];
-        const long long B = (long long)r.hi - r.lo;
-        if (B <= 0) { pickD[(size_t)i] = cands.back().D; continue; }   // empty band: zero row, cheapest group
-        const long long jmax = B - B / 2;
+        const RowProfile& rp = prof[(size_t)i];
+        const long long B = rp.rhi - rp.rlo;
+        if (rp.pos.empty() || B <= 0) { pickD[(size_t)i] = cands.back(); continue; }   // empty band: zero row, cheapest group
         double best = cm.engine * 0.92;   // switch only for a clear gain
-        for (const Cand& c : cands) {
-            if (2 * jmax * 51 > c.M * 50) continue;   // oversampling >= 1.02
-            int K; double beta, err;
-            // the estimate of kb_design's first loop is enough to rank; the group's kernel is verified below
-            const double os = (double)c.M / (2.0 * (double)jmax);
-            const double PI = 3.14159265358979323846;
-            int k = 4;
-            for (; k <= kmax; ++k) {
-                const double y = PI * k * sqrt(1.0 - 1.0 / os);
-                if (2.0 * y * exp(-y) <= 3.0 * tol) break;
-            }
-            if (k > kmax) continue;
-            (void)K; (void)beta; (void)err;
-            const double cost = cm.engine / c.D + cm.fir0 + cm.fir_tap * k;
-            if (cost < best) { best = cost; pickD[(size_t)i] = c.D; }
+        for (int D : cands) {
+            const long long M = N / D;
+            if (B + 2 > M) continue;
+            int K, b; double err;
+            if (!design(D, std::vector<int>{i}, K, b, err)) continue;
+            const bool vec = resample_is_vec(hp.dtype, D);
+            const double cost = cm.engine / D + (vec ? cm.fir0 + cm.fir_tap * K : cm.firs0 + cm.firs_tap * K);
+            if (cost < best) { best = cost; pickD[(size_t)i] = D; }
         }
     }
     bool any = false;
     for (int d : pickD) any = any || d > 1;
     if (!any) return;
     // groups by decimation, exact rows (D = 1) last
-    std::vector<int> Ds;
-    for (const Cand& c : cands) Ds.push_back(c.D);
+    std::vector<int> Ds(cands);
     std::sort(Ds.begin(), Ds.end(), [](int a, int b) { return a > b; });
     Ds.push_back(1);
     for (size_t di = 0; di < Ds.size(); ++di) {
@@ -844,13 +955,15 @@ inline void plan_multirate(HostPlan& hp) {
         g.D = D;
         for (int i = 0; i < hp.F; ++i) if (pickD[(size_t)i] == D) g.fidx.push_back(i);
         if (g.fidx.empty()) continue;
-        g.sub = make_sub_plan(hp, g.fidx, D);
+        std::vector<std::pair<long long, long long>> bands;
+        for (int i : g.fidx) bands.push_back(std::make_pair(prof[(size_t)i].rlo, prof[(size_t)i].rhi));
+        g.sub = make_sub_plan(hp, g.fidx, D, bands);
         bool ok = (bool)g.sub;
         if (ok && D > 1) {
-            long long jmax = 1;
-            for (const FreqRec& r : g.sub->rec) jmax = std::max<long long>(jmax, std::max<long long>(-(long long)r.lo, (long long)r.hi));
-            ok = kb_design(D, N / D, jmax, tol, kmax, hp.dtype == 1, g.K, g.beta, g.err);
+            int bsel = 0;
+            ok = design(D, g.fidx, g.K, bsel, g.err);
             if (ok) {
+                g.beta = fb_of(bsel) * PI * g.K;
                 const double inv = 1.0 / (bessel_i0(g.beta) - 1.0);
                 g.coef.resize((size_t)D * g.K);
                 g.t0.resize((size_t)D);
@@ -860,6 +973,8 @@ inline void plan_multirate(HostPlan& hp) {
                     g.t0[(size_t)p] = t0;
                     for (int t = 0; t < g.K; ++t) g.coef[(size_t)p * g.K + t] = kb_phi(x - (double)(t0 + t), g.K, g.beta, inv);
                 }
+                long long jmax = 1;
+                for (const FreqRec& r : g.sub->rec) jmax = std::max<long long>(jmax, std::max<long long>(-(long long)r.lo, (long long)r.hi));
                 std::vector<long long> bins((size_t)jmax + 1);
                 for (long long j = 0; j <= jmax; ++j) bins[(size_t)j] = j;
                 std::vector<double> H;

@@ -38,7 +38,8 @@ struct ResampleParams {
     int row0;              // first group row (signal-major: row = signal * F + fi) of this launch
     int WR, WP;            // run-warps and phase-warps per run-warp: blockDim = 32 * WR * WP
     int RS;                // staging-tile pitch per run
-    fastdiv dRD;           // x / (R * D)
+    fastdiv dRD;           // x / (R * D)   (vector kernel: x / (R * D / PQ))
+    const T* coefq;        // vector kernel: weights regrouped [D / PQ][K][PQ]
 };
 
 template <typename T, int K, int R> struct ResampleGeo {
@@ -137,6 +138,168 @@ NW_HD void resample_body(const ResampleParams<T>& P, char* smem, int bx, int by,
         const uint32_t jj = fd_div(idx, P.dRD);
         st_stream(out + n, tile[(size_t)jj * P.RS + (idx - jj * RD)]);
     }
+}
+
+// ---- vector kernel ----------------------------------------------------------------------------------------
+// The same interpolation for even tap counts and even decimations, laid out for 16-byte (PQ = 4 outputs, D % 4 == 0) or
+// 8-byte (PQ = 2, D % 2 == 0; fp64: 16 bytes) shared-memory and global accesses:
+//   * a CTA of nthr threads owns C = nthr * R consecutive m of one row; every thread keeps the R + K - 1 samples its run
+//     needs in registers and computes ALL D phases of its run, PQ neighbouring phases at a time (PQ K coefficients in
+//     registers per phase group, loaded with warp-uniform vector loads), so one sample serves PQ outputs per register read;
+//   * the CTA's samples are staged once, linearly, with one pad slot per R samples: staging stores and the per-thread
+//     window loads (lane stride R + 1 slots) are both bank-conflict free;
+//   * results go to a per-thread row of the staging tile (pitch R D + PQ words: conflict free for the PQ-wide stores) and
+//     leave as the CTA's one contiguous piece of the output row in PQ-wide streaming stores, a warp covering
+//     32 PQ consecutive samples per instruction.
+// Per output: K packed FMAs, one |z|^2, and 3 / PQ memory instructions.
+template <typename T, int PQ> struct RsVec { T v[PQ]; };
+#if defined(__CUDA_ARCH__)
+NW_D void rs_st_shared(float* p, const RsVec<float, 4>& r) { *(float4*)p = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]); }
+NW_D void rs_st_shared(float* p, const RsVec<float, 2>& r) { *(float2*)p = make_float2(r.v[0], r.v[1]); }
+NW_D void rs_st_shared(double* p, const RsVec<double, 2>& r) { *(double2*)p = make_double2(r.v[0], r.v[1]); }
+NW_D void rs_st_shared(double* p, const RsVec<double, 4>& r) {
+    *(double2*)p = make_double2(r.v[0], r.v[1]);
+    *(double2*)(p + 2) = make_double2(r.v[2], r.v[3]);
+}
+NW_D void rs_copy_out(float* g, const float* s, RsVec<float, 4>*) { __stcs((float4*)g, *(const float4*)s); }
+NW_D void rs_copy_out(float* g, const float* s, RsVec<float, 2>*) { __stcs((float2*)g, *(const float2*)s); }
+NW_D void rs_copy_out(double* g, const double* s, RsVec<double, 2>*) { __stcs((double2*)g, *(const double2*)s); }
+NW_D void rs_copy_out(double* g, const double* s, RsVec<double, 4>*) {
+    __stcs((double2*)g, *(const double2*)s);
+    __stcs((double2*)(g + 2), *(const double2*)(s + 2));
+}
+template <typename T, int PQ> NW_D RsVec<T, PQ> rs_ld_coef(const T* p);
+template <> NW_D RsVec<float, 4> rs_ld_coef<float, 4>(const float* p) {
+    const float4 v = __ldg((const float4*)p);
+    RsVec<float, 4> r;
+    r.v[0] = v.x; r.v[1] = v.y; r.v[2] = v.z; r.v[3] = v.w;
+    return r;
+}
+template <> NW_D RsVec<float, 2> rs_ld_coef<float, 2>(const float* p) {
+    const float2 v = __ldg((const float2*)p);
+    RsVec<float, 2> r;
+    r.v[0] = v.x; r.v[1] = v.y;
+    return r;
+}
+template <> NW_D RsVec<double, 2> rs_ld_coef<double, 2>(const double* p) {
+    const double2 v = __ldg((const double2*)p);
+    RsVec<double, 2> r;
+    r.v[0] = v.x; r.v[1] = v.y;
+    return r;
+}
+template <> NW_D RsVec<double, 4> rs_ld_coef<double, 4>(const double* p) {
+    const double2 a = __ldg((const double2*)p), b = __ldg((const double2*)p + 1);
+    RsVec<double, 4> r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+    return r;
+}
+#else
+template <typename T, int PQ> inline RsVec<T, PQ> rs_ld_coef(const T* p) { RsVec<T, PQ> r; for (int j = 0; j < PQ; ++j) r.v[j] = p[j]; return r; }
+template <typename T, int PQ> inline void rs_st_shared(T* p, const RsVec<T, PQ>& r) { for (int j = 0; j < PQ; ++j) p[j] = r.v[j]; }
+template <typename T, int PQ> inline void rs_copy_out(T* g, const T* s, RsVec<T, PQ>*) { for (int j = 0; j < PQ; ++j) g[j] = s[j]; }
+#endif
+
+template <typename T, int K, int R, int PQ> struct ResampleVecGeo {
+    static const int WN = R + K - 1;                         // window samples per run (K even: one tap offset for all phases)
+    static NW_HD int pitch(int D) { return R * D + PQ; }     // staging-tile words per thread
+    static NW_HD size_t smem_bytes(int nthr, int D) {
+        const size_t C = (size_t)nthr * R;
+        const size_t ys = (C + K + (C + K) / R + 2) * sizeof(cx<T>);
+        const size_t tile = (size_t)nthr * pitch(D) * sizeof(T);
+        return ys > tile ? ys : tile;
+    }
+};
+
+template <typename T, int K, int R, int PQ, int MODE>
+NW_HD void resample_vec_body(const ResampleParams<T>& P, char* smem, int bx, int by, int tid, int nthr) {
+    typedef ResampleVecGeo<T, K, R, PQ> G;
+    static_assert((K & 1) == 0 && (R & (R - 1)) == 0, "even taps, power-of-two runs");
+    const int D = P.D, M = P.M;
+    const int C = nthr * R;
+    const long long m0 = (long long)bx * C;
+    const int gr = P.row0 + by, si = gr / P.F, fi = gr - si * P.F;
+    const size_t orow = (size_t)si * (size_t)P.F_out + (size_t)(P.fmap ? P.fmap[fi] : fi);
+    T* out = (T*)P.out + orow * (size_t)P.N;
+    const cx<T>* y = P.y + (size_t)by * (size_t)P.ystride;
+    cx<T>* ys = (cx<T>*)smem;
+    T* tile = (T*)smem;
+    // stage samples m0 + t0 + i, i < C + K - 1 (t0 = 1 - K / 2, indices mod M) at slot i + i / R
+    {
+        long long mi = (m0 + (1 - K / 2) + tid) % M;
+        if (mi < 0) mi += M;
+        const int adv = nthr % M;
+        for (int i = tid; i < C + K - 1; i += nthr) {
+            ys[i + i / R] = y[mi];
+            mi += adv;
+            if (mi >= M) mi -= M;
+        }
+    }
+    NW_SYNC();
+    cx<T> w[G::WN];
+    {
+        const cx<T>* yb = ys + (size_t)tid * (R + 1);
+#pragma unroll
+        for (int o = 0; o < G::WN; ++o) w[o] = yb[o + o / R];
+    }
+    NW_SYNC();   // every window is in registers: the tile may overwrite the staged samples
+    const int RS = G::pitch(D);
+    T* dst = tile + (size_t)tid * RS;
+    const T* cq = P.coefq;
+    for (int p0 = 0; p0 < D; p0 += PQ, cq += K * PQ) {
+        RsVec<T, PQ> c[K];
+#pragma unroll
+        for (int t = 0; t < K; ++t) c[t] = rs_ld_coef<T, PQ>(cq + t * PQ);
+#pragma unroll
+        for (int mm = 0; mm < R; ++mm) {
+            RsVec<T, PQ> r;
+#pragma unroll
+            for (int j = 0; j < PQ; ++j) {
+                // one accumulator per output: the PQ R outputs of a phase group are independent chains
+                cx<T> a = mk<T>((T)0, (T)0);
+#pragma unroll
+                for (int t = 0; t < K; ++t) rs_fma(a, w[mm + t], c[t].v[j]);
+                r.v[j] = real_out<T>(MODE, a);
+            }
+            rs_st_shared(dst + mm * D + p0, r);
+        }
+    }
+    NW_SYNC();
+    // the CTA's outputs n = m0 D + PQ v, v < C D / PQ, are one contiguous piece of the row; thread row jj holds R D of them
+    const uint32_t total = (uint32_t)C * (uint32_t)D / PQ;
+    const uint32_t rowv = (uint32_t)R * (uint32_t)D / PQ;
+    const long long n0 = m0 * D;
+    for (uint32_t v = tid; v < total; v += nthr) {
+        const long long n = n0 + (long long)v * PQ;
+        if (n >= P.N) break;
+        const uint32_t jj = fd_div(v, P.dRD);
+        rs_copy_out(out + n, tile + (size_t)jj * RS + (size_t)(v - jj * rowv) * PQ, (RsVec<T, PQ>*)nullptr);
+    }
+}
+
+// run length of the vector kernel by decimation: R D stays near 64 outputs per thread (tile <= 33 KB per 128 threads, so
+// that six CTAs share an SM), window overhead (R + K - 1) / R is paid once per D outputs
+inline int resample_vec_run(int D) { return D <= 4 ? 16 : D <= 8 ? 8 : D <= 16 ? 4 : 2; }
+
+// host-side launch geometry of the vector kernel for a group (D, K) at decimated length M; false: not eligible
+// (odd D or K, or a tap count / precision the vector kernels are not compiled for - the scalar kernel takes those)
+struct ResampleVecShape { int R, PQ, nthr, C; unsigned tiles; size_t smem; fastdiv dRD; };
+template <typename T> inline bool resample_vec_shape(int D, int K, long long M, ResampleVecShape& v) {
+    if (sizeof(T) != 4 || (D & 1) || (K & 1) || K < 4 || K > 12) return false;
+    v.R = resample_vec_run(D);
+    v.PQ = (D & 3) ? 2 : 4;
+    v.nthr = 128;
+    v.C = v.nthr * v.R;
+    v.tiles = (unsigned)((M + v.C - 1) / v.C);
+    const size_t ys = ((size_t)v.C + K + ((size_t)v.C + K) / v.R + 2) * 2 * sizeof(T);
+    const size_t tile = (size_t)v.nthr * ((size_t)v.R * D + v.PQ) * sizeof(T);
+    v.smem = ys > tile ? ys : tile;
+    v.dRD = make_fastdiv((uint32_t)(v.R * D / v.PQ));
+    return true;
+}
+// weights regrouped for the vector kernel: coefq[(p / PQ) K + t][p % PQ] = coef[p][t]
+template <typename T> inline void resample_coefq(const double* coef, int D, int K, int PQ, T* q) {
+    for (int p = 0; p < D; ++p)
+        for (int t = 0; t < K; ++t) q[((size_t)(p / PQ) * K + t) * PQ + (p % PQ)] = (T)coef[(size_t)p * K + t];
 }
 
 // run length per lane (compile-time: the window lives in registers)

@@ -94,7 +94,7 @@ struct nwcwt_plan {
     // resampled rows (HostPlan::groups): one sub-plan per group, plus the group's interpolation tables
     struct Group {
         nwcwt_plan* sub = nullptr;
-        void *d_coef = nullptr, *d_eq = nullptr;
+        void *d_coef = nullptr, *d_eq = nullptr, *d_coefq = nullptr;   // coefq: weights regrouped for the vector kernel
         int *d_t0 = nullptr, *d_fmap = nullptr;
         int t0min = 0;
     };
@@ -196,6 +196,27 @@ template <> struct Long2Dispatch<double> {
     }
 };
 
+// vector interpolation kernels (nw_resample.cuh: resample_vec_body) exist in fp32 only
+template <typename T> struct RsVecDispatch {
+    static cudaError_t prepare() { return cudaSuccess; }
+    static cudaError_t run(int, int, int, int, const ResampleParams<T>&, dim3, size_t, cudaStream_t) { return cudaErrorInvalidValue; }
+};
+template <> struct RsVecDispatch<float> {
+    static cudaError_t prepare() {
+        cudaError_t e;
+        if ((e = prepare_resample_vec<float, 4, OUT_POWER>()) != cudaSuccess) return e;
+        if ((e = prepare_resample_vec<float, 4, OUT_ABS>()) != cudaSuccess) return e;
+        if ((e = prepare_resample_vec<float, 2, OUT_POWER>()) != cudaSuccess) return e;
+        return prepare_resample_vec<float, 2, OUT_ABS>();
+    }
+    static cudaError_t run(int PQ, int mode, int K, int R, const ResampleParams<float>& P, dim3 g, size_t sm, cudaStream_t s) {
+        if (PQ == 4) return mode == OUT_POWER ? launch_resample_vec<float, 4, OUT_POWER>(K, R, P, g, sm, s)
+                                              : launch_resample_vec<float, 4, OUT_ABS>(K, R, P, g, sm, s);
+        return mode == OUT_POWER ? launch_resample_vec<float, 2, OUT_POWER>(K, R, P, g, sm, s)
+                                 : launch_resample_vec<float, 2, OUT_ABS>(K, R, P, g, sm, s);
+    }
+};
+
 template <typename T>
 static int upload_tw(void** dptr, long long count, long long P, long long step) {
     std::vector<cx<T>> v;
@@ -281,7 +302,15 @@ static int ensure_device_t(nwcwt_plan* pl) {
         CUDA_TRY(cudaMalloc((void**)&g.d_fmap, sizeof(int) * mg.fidx.size()));
         CUDA_TRY(cudaMemcpy(g.d_fmap, mg.fidx.data(), sizeof(int) * mg.fidx.size(), cudaMemcpyHostToDevice));
         if (mg.D > 1) {
-            if (!has_resample<T>(mg.K)) return fail(NWCWT_ERR_UNSUPPORTED, "no interpolation kernel for this tap count");
+            ResampleVecShape vs;
+            const bool vec = resample_vec_shape<T>(mg.D, mg.K, g.sub->hp.N, vs);
+            if (!vec && !has_resample<T>(mg.K)) return fail(NWCWT_ERR_UNSUPPORTED, "no interpolation kernel for this tap count");
+            if (vec) {
+                std::vector<T> q(mg.coef.size());
+                resample_coefq<T>(mg.coef.data(), mg.D, mg.K, vs.PQ, q.data());
+                CUDA_TRY(cudaMalloc(&g.d_coefq, sizeof(T) * q.size()));
+                CUDA_TRY(cudaMemcpy(g.d_coefq, q.data(), sizeof(T) * q.size(), cudaMemcpyHostToDevice));
+            }
             std::vector<T> c(mg.coef.begin(), mg.coef.end()), e(mg.eq.begin(), mg.eq.end());
             CUDA_TRY(cudaMalloc(&g.d_coef, sizeof(T) * c.size()));
             CUDA_TRY(cudaMemcpy(g.d_coef, c.data(), sizeof(T) * c.size(), cudaMemcpyHostToDevice));
@@ -292,7 +321,10 @@ static int ensure_device_t(nwcwt_plan* pl) {
             g.t0min = *std::min_element(mg.t0.begin(), mg.t0.end());
         }
     }
-    if (!pl->groups.empty()) CUDA_TRY(prepare_resample<T>());
+    if (!pl->groups.empty()) {
+        CUDA_TRY(prepare_resample<T>());
+        CUDA_TRY(RsVecDispatch<T>::prepare());
+    }
     pl->on_device = true;
     return 0;
 }
@@ -499,7 +531,10 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
     if (!Long2Dispatch<T>::has(eh.cfgB, 1, spB)) spB = 0;
     ResampleParams<T> R;
     ResampleShape shp{1, 1, 0, 0, 0};
+    ResampleVecShape vshp;
+    bool vec = false;
     if (D > 1) {
+        vec = resample_vec_shape<T>(D, mg->K, eh.N, vshp) && dg->d_coefq;
         shp = resample_shape<T>(D, mg->K);
         memset(&R, 0, sizeof(R));
         R.ystride = eh.N;
@@ -516,7 +551,8 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
         R.WR = shp.WR;
         R.WP = shp.WP;
         R.RS = shp.RS;
-        R.dRD = make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
+        R.dRD = vec ? vshp.dRD : make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
+        R.coefq = (const T*)dg->d_coefq;
         Q.eq = (const T*)dg->d_eq;
         Q.out_mode = NWCWT_OUT_CWT;
     } else {
@@ -543,7 +579,8 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
             R.row0 = (int)r0;
             const unsigned tiles = (unsigned)((eh.N + shp.C - 1) / shp.C);
             LaunchScope ls(6, st);
-            CUDA_TRY(launch_resample<T>(mg->K, output, R, dim3(tiles, g), 32 * shp.WR * shp.WP, shp.smem, st));
+            if (vec) CUDA_TRY(RsVecDispatch<T>::run(vshp.PQ, output, mg->K, vshp.R, R, dim3(vshp.tiles, g), vshp.smem, st));
+            else CUDA_TRY(launch_resample<T>(mg->K, output, R, dim3(tiles, g), 32 * shp.WR * shp.WP, shp.smem, st));
         }
     }
     (void)esz;
@@ -774,7 +811,7 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
     for (nwcwt_plan::Group& g : pl->groups) {
         if (g.sub && g.sub->on_device) {
             cudaSetDevice(pl->hp.device);
-            void* ptrs[] = {g.d_coef, g.d_eq, g.d_t0, g.d_fmap};
+            void* ptrs[] = {g.d_coef, g.d_eq, g.d_t0, g.d_fmap, g.d_coefq};
             for (void* q : ptrs) if (q) cudaFree(q);
         }
         nwcwt_plan_destroy(g.sub);

@@ -108,6 +108,17 @@ static void resample_launch(const ResampleParams<T>& R, int mode, char* smp, int
         });
 }
 
+template <typename T, int K, int PQ>
+static void resample_vec_launch(const ResampleParams<T>& R, int mode, char* smp, const ResampleVecShape& v, int g) {
+    for (int y = 0; y < g; ++y) for (int x = 0; x < (int)v.tiles; ++x)
+        Fibers::get().run(v.nthr, [&](int t) {
+#define RV(r) case r: if (mode == OUT_POWER) resample_vec_body<T, K, r, PQ, OUT_POWER>(R, smp, x, y, t, v.nthr); \
+                      else resample_vec_body<T, K, r, PQ, OUT_ABS>(R, smp, x, y, t, v.nthr); break;
+            switch (v.R) { RV(16) RV(8) RV(4) RV(2) }
+#undef RV
+        });
+}
+
 // Inverse transforms of gs signals x the frequencies of plan eh (the main plan, or the sub-plan of group mg) on the
 // packed kernels, followed by the interpolation kernel for a resampled group: mirrors nwcwt.cu: inverse_rows.
 template <typename T>
@@ -131,8 +142,12 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* m
     std::vector<T> eq, coef;
     ResampleParams<T> R;
     ResampleShape shp{1, 1, 0, 0, 0};
+    ResampleVecShape vshp;
+    bool vec = false;
+    std::vector<T> coefq;
     memset(&R, 0, sizeof(R));
     if (D > 1) {
+        vec = resample_vec_shape<T>(D, mg->K, eh.N, vshp);
         eq.assign(mg->eq.begin(), mg->eq.end());
         coef.assign(mg->coef.begin(), mg->coef.end());
         Y.resize((size_t)ring2 * eh.N);
@@ -141,6 +156,12 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* m
         R.t0min = *std::min_element(mg->t0.begin(), mg->t0.end());
         R.fmap = mg->fidx.data(); R.F = eh.F; R.F_out = hp.F; R.WR = shp.WR; R.WP = shp.WP; R.RS = shp.RS;
         R.dRD = make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
+        if (vec) {
+            coefq.resize(coef.size());
+            resample_coefq<T>(mg->coef.data(), D, mg->K, vshp.PQ, coefq.data());
+            R.coefq = coefq.data();
+            R.dRD = vshp.dRD;
+        }
         Q.eq = eq.data();
         Q.out_mode = OUT_CWT;
     } else {
@@ -148,7 +169,7 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* m
         if (mg) { Q.fmap = mg->fidx.data(); Q.F_out = hp.F; }
     }
     const int tA = (eh.N2f + (2 << eh.tpshA) - 1) / (2 << eh.tpshA), tB = (eh.N1f + (2 << eh.tpshB) - 1) / (2 << eh.tpshB);
-    std::vector<char> sm2(std::max(std::max(eh.smem_A2, eh.smem_B2), shp.smem) + 64);
+    std::vector<char> sm2(std::max(std::max(std::max(eh.smem_A2, eh.smem_B2), shp.smem), vec ? vshp.smem : (size_t)0) + 64);
     char* smp = (char*)(((uintptr_t)sm2.data() + 31) & ~(uintptr_t)31);
     const int ntA = (g_mode & 4) ? 1 : eh.nthrA2, ntB = (g_mode & 4) ? 1 : eh.nthrB2;
     const long long rows = (long long)gs * eh.F;
@@ -179,7 +200,15 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* m
         if (D > 1) {
             R.y = Y.data(); R.row0 = (int)r0;
             const int tiles = (int)((eh.N + shp.C - 1) / shp.C), nt = 32 * shp.WR * shp.WP;
-            switch (mg->K) {
+            if (vec) {
+                switch (mg->K * 10 + vshp.PQ) {
+#define RV_CASE(k) case k * 10 + 4: resample_vec_launch<T, k, 4>(R, output, smp, vshp, g); break; \
+                   case k * 10 + 2: resample_vec_launch<T, k, 2>(R, output, smp, vshp, g); break;
+                    RV_CASE(4) RV_CASE(6) RV_CASE(8) RV_CASE(10) RV_CASE(12)
+#undef RV_CASE
+                    default: return -2;
+                }
+            } else switch (mg->K) {
 #define RS_CASE(k) case k: resample_launch<T, k>(R, output, smp, tiles, g, nt); break;
                 RS_CASE(4) RS_CASE(5) RS_CASE(6) RS_CASE(7) RS_CASE(8) RS_CASE(9) RS_CASE(10) RS_CASE(11) RS_CASE(12) RS_CASE(13)
                 RS_CASE(14) RS_CASE(15) RS_CASE(16) RS_CASE(18) RS_CASE(20) RS_CASE(22) RS_CASE(24)
