@@ -29,6 +29,7 @@ struct FreqRec {
     double freq;    // analysis frequency (Hz)
     double aux;     // Morlet: peak_freq(freq)
     double kx;      // fp32 path: x = (k - grid_off) * kx   (df/freq [* peak])
+    long long woff; // long rows: index of the band's first bin in the plan's weight table (SpecParams::wtab)
 };
 
 template <typename T>
@@ -41,6 +42,10 @@ struct SpecParams {
     const FreqRec* rec;  // [F] device
     const cx<T>* table;  // TABLE: [F][table_len]
     long long table_len; // row pitch of the table
+    // long rows, analytic families: the band of every frequency evaluated ONCE per plan (all signals share it) -
+    // wtab[rec.woff + (j - rec.lo)] = W_f at transform bin j, times norm and, in a resampled group, the equaliser.
+    // nullptr: evaluate in registers (bands too large to tabulate).
+    const T* wtab;
 };
 
 NW_HD float nw_exp(float x) { return expf(x); }

@@ -160,6 +160,12 @@ template <typename T>
 NW_HD cx2<T> passA2_bins(const Long2Params<T>& P, const FreqRec& rec, int fi, const cx<T>* X, int k1s, int k2) {
     const int j = k1s * P.N2 + k2;
     cx<T> a = mk<T>((T)0, (T)0), b = a;
+    if (P.sp.wtab) {   // tabulated weights (equaliser folded in)
+        const T* wt = P.sp.wtab + rec.woff - rec.lo;
+        if (k2 < P.N2 && j >= rec.lo && j < rec.hi) a = scale(X[j + rec.shift], wt[j]);
+        if (k2 + 1 < P.N2 && j + 1 >= rec.lo && j + 1 < rec.hi) b = scale(X[j + 1 + rec.shift], wt[j + 1]);
+        return mk2<T>(a, b);
+    }
     if (k2 < P.N2 && j >= rec.lo && j < rec.hi) {
         a = spec_times<T>(P.sp, rec, fi, j + rec.shift, X[j + rec.shift]);
         if (P.eq) a = scale(a, P.eq[j < 0 ? -j : j]);
@@ -225,6 +231,21 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         }
         if constexpr (SP == 0) fft2_dit<T, +1, FromBuf, TmDst2<T>, true>(P.stA, seq_pow2(tpsh), P.twA, buf, FromBuf(), dst, tid, nthr);
         else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2, TmDst2<T>, true>(P.twA, buf, dst, tid, nthr);
+        return;
+    }
+    if (2 * nk1 >= N1) {
+        // wide band (the decimated transforms of resampled rows): one sweep over the whole tile - row k1 holds the bin of
+        // the window [k1lo, k1lo + N1) that is congruent to it, or zero (passA2_bins checks the band)
+        for (int i = tid; i < (N1 << tpsh); i += nthr) {
+            const int tp = i & (TP - 1);
+            const int k1 = i >> tpsh;
+            int u = (k1 - k1lo) % N1;
+            if (u < 0) u += N1;
+            buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1lo + u, c + 2 * tp);
+        }
+        NW_SYNC();
+        if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
+        else fft2_dit_static<T, +1, S::TPS, (SP ? S::P : 4), (SP ? S::R0 : 2), (SP ? S::R1 : 2), S::R2>(P.twA, buf, dst, tid, nthr);
         return;
     }
     const cx2<T> z = zero2<T>();

@@ -325,6 +325,7 @@ inline void plan_bands(HostPlan& hp) {
         long long lo, hi;
         r.toff = 0;
         r.shift = 0;
+        r.woff = 0;
         if (hp.family == FAM_TABLE) {
             // pad_to, base.py:75-82: truncate, or centre with the short half in front
             const long long m = hp.table_lens.empty() ? hp.table_len : hp.table_lens[i];
@@ -453,15 +454,20 @@ inline void plan_shape_fast(HostPlan& hp) {
             Fft2Plan a, b;
             if (!plan_packed(n1, a) || !plan_packed(n2, b)) continue;
             const int fa = env_int("NWCWT_TPSH_A", -1), fb = env_int("NWCWT_TPSH_B", -1);   // tuning overrides
-            for (int ta = 2; ta >= 0; --ta)
-                for (int tb = 2; tb >= 0; --tb) {
+            for (int ta = 4; ta >= 0; --ta)
+                for (int tb = 4; tb >= 0; --tb) {
                     if ((fa >= 0 && ta != fa) || (fb >= 0 && tb != fb)) continue;
+                    // 8 and 16 lane pairs per tile only for short transforms (the decimated lengths of resampled rows split
+                    // into factors of 75 .. 250): tiles of up to 2048 two-lane values, so that a CTA has enough butterflies
+                    // per stage to fill its warps
+                    if ((ta > 2 && ((size_t)n1 << ta) > 2048) || (tb > 2 && ((size_t)n2 << tb) > 2048)) continue;
+                    if ((ta > 2 || tb > 2) && !env_int("NWCWT_BIG_TILES", 0)) continue;   // measured slower on cfg2's decimated lengths (profiles/r02)
                     const size_t ba = ((size_t)n1 << ta) * 2 * cs, bb = ((size_t)n2 << tb) * 2 * cs + 16;
                     const int ca = ctas(ba), cb = ctas(bb);
                     if (!ca || !cb) continue;
                     // lane pairs per tile: the step from one pair to two is worth more than from two to four
                     // (measured: fp64 2^20, 1024 x 1024 with two pairs each beats 2048 x 512 with one and four)
-                    static const double TPS_SCORE[3] = {0.0, 120.0, 200.0};
+                    static const double TPS_SCORE[5] = {0.0, 120.0, 200.0, 260.0, 300.0};
                     // resident CTAs matter more to pass A, the run length of the intermediate more to pass B (measured: 2^24 fp32
                     // and 2^22 fp64 are fastest with one pair / three CTAs in pass A and two pairs / one CTA in pass B)
                     double score = TPS_SCORE[ta] + TPS_SCORE[tb] + 80.0 * ca + 55.0 * cb - 40.0 * (a.nst + b.nst);
@@ -857,6 +863,31 @@ inline std::shared_ptr<HostPlan> make_sub_plan(const HostPlan& hp, const std::ve
     if (!s.fast) return nullptr;
     plan_narrow(s);
     return sp;
+}
+
+// Weight table of a long-row plan of an analytic family (SpecParams::wtab): every frequency's band evaluated once, with
+// the very formulas the kernels would use per bin (SpecEval<T>), times norm and the group's equaliser eq[|j|] (or null).
+// Sets FreqRec::woff; false (and no table) when the bands hold more than max_bytes.
+template <typename T>
+inline bool build_weight_table(HostPlan& hp, const double* eq, size_t max_bytes, std::vector<T>& tab) {
+    tab.clear();
+    if (hp.family == FAM_TABLE || hp.F <= 0) return false;
+    long long total = 0;
+    for (FreqRec& r : hp.rec) { r.woff = total; total += std::max(0, r.hi - r.lo); }
+    if (total <= 0 || (size_t)total * sizeof(T) > max_bytes) return false;
+    tab.resize((size_t)total);
+    SpecParams<T> sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.family = hp.family; sp.grid_off = hp.grid_off; sp.df = hp.df; sp.p0 = hp.p0; sp.p1 = hp.p1;
+    sp.p2 = hp.family == FAM_MORSE ? hp.p0 / hp.p1 : hp.p2;
+    sp.norm = (T)(1.0 / (double)hp.data_len());
+    for (const FreqRec& r : hp.rec)
+        for (int j = r.lo; j < r.hi; ++j) {
+            T w = SpecEval<T>::real(sp, r, j + r.shift);
+            if (eq) w *= (T)eq[j < 0 ? -j : j];
+            tab[(size_t)(r.woff + (j - r.lo))] = w;
+        }
+    return true;
 }
 
 // cost model, picoseconds per OUTPUT sample on B200 (profiles/r02): engine = the packed two-pass transform per point of

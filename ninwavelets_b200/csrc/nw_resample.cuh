@@ -37,9 +37,11 @@ struct ResampleParams {
     int F, F_out;
     int row0;              // first group row (signal-major: row = signal * F + fi) of this launch
     int WR, WP;            // run-warps and phase-warps per run-warp: blockDim = 32 * WR * WP
-    int RS;                // staging-tile pitch per run
+    int RS;                // staging-tile pitch per run   (vector kernel: bytes of a run-warp group's shared-memory region)
     fastdiv dRD;           // x / (R * D)   (vector kernel: x / (R * D / PQ))
     const T* coefq;        // vector kernel: weights regrouped [D / PQ][K][PQ]
+    fastdiv dGT;           // vector kernel: x / (work items per row = ceil(M / (32 R)))
+    int nrows;             // vector kernel: rows of this launch
 };
 
 template <typename T, int K, int R> struct ResampleGeo {
@@ -142,32 +144,27 @@ NW_HD void resample_body(const ResampleParams<T>& P, char* smem, int bx, int by,
 
 // ---- vector kernel ----------------------------------------------------------------------------------------
 // The same interpolation for even tap counts and even decimations, laid out for 16-byte (PQ = 4 outputs, D % 4 == 0) or
-// 8-byte (PQ = 2, D % 2 == 0; fp64: 16 bytes) shared-memory and global accesses:
-//   * a CTA of nthr threads owns C = nthr * R consecutive m of one row; every thread keeps the R + K - 1 samples its run
-//     needs in registers and computes ALL D phases of its run, PQ neighbouring phases at a time (PQ K coefficients in
-//     registers per phase group, loaded with warp-uniform vector loads), so one sample serves PQ outputs per register read;
-//   * the CTA's samples are staged once, linearly, with one pad slot per R samples: staging stores and the per-thread
+// 8-byte (PQ = 2) shared-memory and global accesses:
+//   * a CTA of 128 threads = WR run-warp groups x WP phase-warps owns C = 32 WR R consecutive m of one row; the groups
+//     are independent of each other (own barrier), so their load / arithmetic / store phases interleave.  A lane of a
+//     run-warp owns a run of R consecutive m and keeps the R + K - 1 samples it needs in registers; the WP phase-warps of
+//     a run-warp share the D / PQ phase groups (PQ neighbouring phases) between them, so one sample register serves
+//     PQ D / WP outputs and the PQ K weights of a phase group (warp-uniform vector loads) serve 32 R PQ outputs;
+//   * outputs are accumulated as PAIRS of neighbouring phases: (re, re') and (im, im') in one packed register each,
+//     FFMA2(sample broadcast, weight pair, acc) - K packed FMAs and one packed |z|^2 per output;
+//   * the CTA's samples are staged once, linearly, with one pad slot per R samples: staging stores and the per-lane
 //     window loads (lane stride R + 1 slots) are both bank-conflict free;
-//   * results go to a per-thread row of the staging tile (pitch R D + PQ words: conflict free for the PQ-wide stores) and
-//     leave as the CTA's one contiguous piece of the output row in PQ-wide streaming stores, a warp covering
-//     32 PQ consecutive samples per instruction.
-// Per output: K packed FMAs, one |z|^2, and 3 / PQ memory instructions.
+//   * results go to a per-run row of the staging tile (pitch R D + PQ words: conflict free for the PQ-wide stores) and
+//     leave as the CTA's one contiguous piece of the output row, a warp copying one run's R D samples at a time in
+//     PQ-wide streaming stores (512 contiguous bytes per instruction).
 template <typename T, int PQ> struct RsVec { T v[PQ]; };
 #if defined(__CUDA_ARCH__)
 NW_D void rs_st_shared(float* p, const RsVec<float, 4>& r) { *(float4*)p = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]); }
 NW_D void rs_st_shared(float* p, const RsVec<float, 2>& r) { *(float2*)p = make_float2(r.v[0], r.v[1]); }
 NW_D void rs_st_shared(double* p, const RsVec<double, 2>& r) { *(double2*)p = make_double2(r.v[0], r.v[1]); }
-NW_D void rs_st_shared(double* p, const RsVec<double, 4>& r) {
-    *(double2*)p = make_double2(r.v[0], r.v[1]);
-    *(double2*)(p + 2) = make_double2(r.v[2], r.v[3]);
-}
 NW_D void rs_copy_out(float* g, const float* s, RsVec<float, 4>*) { __stcs((float4*)g, *(const float4*)s); }
 NW_D void rs_copy_out(float* g, const float* s, RsVec<float, 2>*) { __stcs((float2*)g, *(const float2*)s); }
 NW_D void rs_copy_out(double* g, const double* s, RsVec<double, 2>*) { __stcs((double2*)g, *(const double2*)s); }
-NW_D void rs_copy_out(double* g, const double* s, RsVec<double, 4>*) {
-    __stcs((double2*)g, *(const double2*)s);
-    __stcs((double2*)(g + 2), *(const double2*)(s + 2));
-}
 template <typename T, int PQ> NW_D RsVec<T, PQ> rs_ld_coef(const T* p);
 template <> NW_D RsVec<float, 4> rs_ld_coef<float, 4>(const float* p) {
     const float4 v = __ldg((const float4*)p);
@@ -187,114 +184,231 @@ template <> NW_D RsVec<double, 2> rs_ld_coef<double, 2>(const double* p) {
     r.v[0] = v.x; r.v[1] = v.y;
     return r;
 }
-template <> NW_D RsVec<double, 4> rs_ld_coef<double, 4>(const double* p) {
-    const double2 a = __ldg((const double2*)p), b = __ldg((const double2*)p + 1);
-    RsVec<double, 4> r;
-    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
-    return r;
+// two neighbouring phases of one output sample m: acc over the K taps, then |z|^2 (or |z|) of both
+template <int K, int MODE>
+NW_D void rs_pair(const cx<float>* w, const float* c0, int cstride, float& o0, float& o1) {
+    float2 are = make_float2(0.f, 0.f), aim = are;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        const float2 cp = make_float2(c0[t * cstride], c0[t * cstride + 1]);
+        are = __ffma2_rn(make_float2(w[t].x, w[t].x), cp, are);
+        aim = __ffma2_rn(make_float2(w[t].y, w[t].y), cp, aim);
+    }
+    if (MODE == OUT_POWER) {
+        const float2 p = __ffma2_rn(aim, aim, __fmul2_rn(are, are));
+        o0 = p.x;
+        o1 = p.y;
+    } else {
+        o0 = nw_hypot(are.x, aim.x);
+        o1 = nw_hypot(are.y, aim.y);
+    }
+}
+template <int K, int MODE>
+NW_D void rs_pair(const cx<double>* w, const double* c0, int cstride, double& o0, double& o1) {
+    double r0 = 0, i0 = 0, r1 = 0, i1 = 0;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        const double ca = c0[t * cstride], cb = c0[t * cstride + 1];
+        r0 = fma(w[t].x, ca, r0); i0 = fma(w[t].y, ca, i0);
+        r1 = fma(w[t].x, cb, r1); i1 = fma(w[t].y, cb, i1);
+    }
+    o0 = real_out<double>(MODE, mk<double>(r0, i0));
+    o1 = real_out<double>(MODE, mk<double>(r1, i1));
 }
 #else
 template <typename T, int PQ> inline RsVec<T, PQ> rs_ld_coef(const T* p) { RsVec<T, PQ> r; for (int j = 0; j < PQ; ++j) r.v[j] = p[j]; return r; }
 template <typename T, int PQ> inline void rs_st_shared(T* p, const RsVec<T, PQ>& r) { for (int j = 0; j < PQ; ++j) p[j] = r.v[j]; }
 template <typename T, int PQ> inline void rs_copy_out(T* g, const T* s, RsVec<T, PQ>*) { for (int j = 0; j < PQ; ++j) g[j] = s[j]; }
+template <int K, int MODE, typename T>
+inline void rs_pair(const cx<T>* w, const T* c0, int cstride, T& o0, T& o1) {
+    T r0 = 0, i0 = 0, r1 = 0, i1 = 0;
+    for (int t = 0; t < K; ++t) {
+        const T ca = c0[t * cstride], cb = c0[t * cstride + 1];
+        r0 += w[t].x * ca; i0 += w[t].y * ca;
+        r1 += w[t].x * cb; i1 += w[t].y * cb;
+    }
+    o0 = real_out<T>(MODE, mk<T>(r0, i0));
+    o1 = real_out<T>(MODE, mk<T>(r1, i1));
+}
 #endif
 
-template <typename T, int K, int R, int PQ> struct ResampleVecGeo {
-    static const int WN = R + K - 1;                         // window samples per run (K even: one tap offset for all phases)
-    static NW_HD int pitch(int D) { return R * D + PQ; }     // staging-tile words per thread
-    static NW_HD size_t smem_bytes(int nthr, int D) {
-        const size_t C = (size_t)nthr * R;
-        const size_t ys = (C + K + (C + K) / R + 2) * sizeof(cx<T>);
-        const size_t tile = (size_t)nthr * pitch(D) * sizeof(T);
-        return ys > tile ? ys : tile;
-    }
-};
+// barrier among the 32 WP threads of one run-warp group.  (WR, WP) is (4, 1), (2, 2) or (1, 4): a warp-level barrier, the
+// hardware barriers 1 and 2 with 64 threads each, or the CTA barrier - compile-time barrier ids, so that a CTA reserves
+// three hardware barriers and not all sixteen.  The host emulation steps whole CTAs.
+#if defined(__CUDA_ARCH__)
+NW_D void rs_group_sync(int wr, int WP, int WR) {
+    if (WP == 1) __syncwarp();
+    else if (WR == 1) __syncthreads();
+    else if (wr == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else asm volatile("bar.sync 2, 64;" ::: "memory");
+}
+#else
+inline void rs_group_sync(int, int, int) { NW_SYNC(); }
+#endif
 
 template <typename T, int K, int R, int PQ, int MODE>
-NW_HD void resample_vec_body(const ResampleParams<T>& P, char* smem, int bx, int by, int tid, int nthr) {
-    typedef ResampleVecGeo<T, K, R, PQ> G;
-    static_assert((K & 1) == 0 && (R & (R - 1)) == 0, "even taps, power-of-two runs");
-    const int D = P.D, M = P.M;
-    const int C = nthr * R;
-    const long long m0 = (long long)bx * C;
-    const int gr = P.row0 + by, si = gr / P.F, fi = gr - si * P.F;
-    const size_t orow = (size_t)si * (size_t)P.F_out + (size_t)(P.fmap ? P.fmap[fi] : fi);
-    T* out = (T*)P.out + orow * (size_t)P.N;
-    const cx<T>* y = P.y + (size_t)by * (size_t)P.ystride;
-    cx<T>* ys = (cx<T>*)smem;
-    T* tile = (T*)smem;
-    // stage samples m0 + t0 + i, i < C + K - 1 (t0 = 1 - K / 2, indices mod M) at slot i + i / R
-    {
-        long long mi = (m0 + (1 - K / 2) + tid) % M;
-        if (mi < 0) mi += M;
-        const int adv = nthr % M;
-        for (int i = tid; i < C + K - 1; i += nthr) {
-            ys[i + i / R] = y[mi];
-            mi += adv;
-            if (mi >= M) mi -= M;
-        }
-    }
-    NW_SYNC();
-    cx<T> w[G::WN];
-    {
-        const cx<T>* yb = ys + (size_t)tid * (R + 1);
+NW_HD void resample_vec_body(const ResampleParams<T>& P, char* smem, int bx, int nbx, int tid, int nthr) {
+    static_assert((K & 1) == 0 && (R & (R - 1)) == 0 && (PQ == 2 || PQ == 4), "even taps, power-of-two runs");
+    const int D = P.D, M = P.M, WP = P.WP, WR = P.WR;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = warp / WP, wp = warp - wr * WP;
+    // Every run-warp group (its WP warps) is independent of the others: own work items, own samples, own staging tile,
+    // own barrier - the groups of an SM drift apart, so that one group's stores overlap another's arithmetic.  A group's
+    // work items are (row, piece of CG = 32 R consecutive m); the CTAs are persistent and stride over the items, and the
+    // samples of the NEXT item are fetched into registers while the current one is computed.
+    const int gthr = 32 * WP, gtid = wp * 32 + lane;
+    const int CG = 32 * R, NS = CG + K - 1;                             // m per item, samples an item needs
+    constexpr int NPF = R + 1;                                          // >= ceil(NS / 32): prefetch registers per thread
+    const uint32_t GT = P.dGT.d;                                        // items per row
+    const uint32_t total = GT * (uint32_t)P.nrows;
+    char* gsm = smem + (size_t)wr * (size_t)P.RS;                       // RS: bytes of a group's region
+    cx<T>* ys = (cx<T>*)gsm;
+    T* tile = (T*)gsm;
+    const int pitch = R * D + PQ;
+    const int G = D / PQ;
+    const int rowv = R * D / PQ;
+    cx<T> pf[NPF];
+    // samples mg0 + t0 + i, i < NS (t0 = 1 - K / 2, indices mod M) of item `it`
+    auto fetch = [&](uint32_t it) {
+        const uint32_t by = it / GT, gt = it - by * GT;
+        const cx<T>* y = P.y + (size_t)by * (size_t)P.ystride;
+        long long base = (long long)gt * CG + (1 - K / 2);
+        if (base < 0) base += M;
 #pragma unroll
-        for (int o = 0; o < G::WN; ++o) w[o] = yb[o + o / R];
-    }
-    NW_SYNC();   // every window is in registers: the tile may overwrite the staged samples
-    const int RS = G::pitch(D);
-    T* dst = tile + (size_t)tid * RS;
-    const T* cq = P.coefq;
-    for (int p0 = 0; p0 < D; p0 += PQ, cq += K * PQ) {
-        RsVec<T, PQ> c[K];
-#pragma unroll
-        for (int t = 0; t < K; ++t) c[t] = rs_ld_coef<T, PQ>(cq + t * PQ);
-#pragma unroll
-        for (int mm = 0; mm < R; ++mm) {
-            RsVec<T, PQ> r;
-#pragma unroll
-            for (int j = 0; j < PQ; ++j) {
-                // one accumulator per output: the PQ R outputs of a phase group are independent chains
-                cx<T> a = mk<T>((T)0, (T)0);
-#pragma unroll
-                for (int t = 0; t < K; ++t) rs_fma(a, w[mm + t], c[t].v[j]);
-                r.v[j] = real_out<T>(MODE, a);
+        for (int q = 0; q < NPF; ++q) {
+            const int i = gtid + q * gthr;
+            if (i < NS) {
+                long long mi = base + i;
+                if (NS <= M) { if (mi >= M) mi -= M; } else mi %= M;
+                pf[q] = y[mi];
             }
-            rs_st_shared(dst + mm * D + p0, r);
         }
-    }
-    NW_SYNC();
-    // the CTA's outputs n = m0 D + PQ v, v < C D / PQ, are one contiguous piece of the row; thread row jj holds R D of them
-    const uint32_t total = (uint32_t)C * (uint32_t)D / PQ;
-    const uint32_t rowv = (uint32_t)R * (uint32_t)D / PQ;
-    const long long n0 = m0 * D;
-    for (uint32_t v = tid; v < total; v += nthr) {
-        const long long n = n0 + (long long)v * PQ;
-        if (n >= P.N) break;
-        const uint32_t jj = fd_div(v, P.dRD);
-        rs_copy_out(out + n, tile + (size_t)jj * RS + (size_t)(v - jj * rowv) * PQ, (RsVec<T, PQ>*)nullptr);
+    };
+    uint32_t cit = (uint32_t)bx;
+    uint32_t it = cit * (uint32_t)WR + (uint32_t)wr;
+    if (it < total) fetch(it);
+    for (; cit * (uint32_t)WR < total; cit += (uint32_t)nbx) {
+        it = cit * (uint32_t)WR + (uint32_t)wr;
+        const bool valid = it < total;
+        // stage the item's samples at slot i + i / R
+#pragma unroll
+        for (int q = 0; q < NPF; ++q) {
+            const int i = gtid + q * gthr;
+            if (valid && i < NS) ys[i + i / R] = pf[q];
+        }
+        rs_group_sync(wr, WP, WR);
+        cx<T> w[R + K - 1];
+        {
+            const cx<T>* yb = ys + (size_t)lane * (R + 1);
+#pragma unroll
+            for (int o = 0; o < R + K - 1; ++o) w[o] = yb[o + o / R];
+        }
+        rs_group_sync(wr, WP, WR);   // every window is in registers: the tile may overwrite the staged samples
+        {
+            const uint32_t nit = (cit + (uint32_t)nbx) * (uint32_t)WR + (uint32_t)wr;
+            if (nit < total) fetch(nit);   // in flight during the arithmetic below
+        }
+        T* dst = tile + (size_t)lane * pitch;
+        for (int g = wp; g < G; g += WP) {
+            const T* cq = P.coefq + (size_t)g * (K * PQ);
+            RsVec<T, PQ> c[K];
+#pragma unroll
+            for (int t = 0; t < K; ++t) c[t] = rs_ld_coef<T, PQ>(cq + t * PQ);
+#pragma unroll
+            for (int mm = 0; mm < R; ++mm) {
+                RsVec<T, PQ> r;
+#ifdef RS_EXP_NOFMA
+#pragma unroll
+                for (int j = 0; j < PQ; ++j) r.v[j] = w[mm + (j & 1)].x * c[j & 1].v[j];
+#else
+#pragma unroll
+                for (int j = 0; j < PQ; j += 2) rs_pair<K, MODE>(w + mm, &c[0].v[j], PQ, r.v[j], r.v[j + 1]);
+#endif
+                rs_st_shared(dst + mm * D + g * PQ, r);
+            }
+        }
+        rs_group_sync(wr, WP, WR);
+        // the item's outputs are one contiguous piece of the row starting at n0 = mg0 D; run jj holds R D of them
+        if (valid) {
+            const uint32_t by = it / GT, gt = it - by * GT;
+            const int gr = P.row0 + (int)by, si = gr / P.F, fi = gr - si * P.F;
+            const size_t orow = (size_t)si * (size_t)P.F_out + (size_t)(P.fmap ? P.fmap[fi] : fi);
+            const long long n0 = (long long)gt * CG * D;
+            T* o0 = (T*)P.out + orow * (size_t)P.N + n0;
+            const uint32_t nv = (uint32_t)CG * (uint32_t)D / PQ;          // vectors of the item
+            const long long left = (P.N - n0) / PQ;                          // vectors up to the end of the row
+            const uint32_t lim = left < (long long)nv ? (uint32_t)left : nv;
+#ifdef RS_EXP_NOST
+            if (tile[gtid] == (T)123.456) o0[gtid] = tile[gtid + 1];
+            if (true) {} else
+#endif
+            if (lim == nv) {
+#pragma unroll 8
+                for (uint32_t v = gtid; v < nv; v += gthr) {
+                    const uint32_t jj = fd_div(v, P.dRD);
+                    rs_copy_out(o0 + (size_t)v * PQ, tile + (size_t)jj * pitch + (size_t)(v - jj * rowv) * PQ, (RsVec<T, PQ>*)nullptr);
+                }
+            } else {   // the row ends inside this item (N is a multiple of D, hence of PQ)
+                for (uint32_t v = gtid; v < lim; v += gthr) {
+                    const uint32_t jj = fd_div(v, P.dRD);
+                    rs_copy_out(o0 + (size_t)v * PQ, tile + (size_t)jj * pitch + (size_t)(v - jj * rowv) * PQ, (RsVec<T, PQ>*)nullptr);
+                }
+            }
+        }
+        rs_group_sync(wr, WP, WR);   // the tile is read: the next item's samples may overwrite it
     }
 }
 
-// run length of the vector kernel by decimation: R D stays near 64 outputs per thread (tile <= 33 KB per 128 threads, so
-// that six CTAs share an SM), window overhead (R + K - 1) / R is paid once per D outputs
-inline int resample_vec_run(int D) { return D <= 4 ? 16 : D <= 8 ? 8 : D <= 16 ? 4 : 2; }
+// resident CTAs per SM the vector kernel's register budget is sized for (__launch_bounds__): window 2 (R + K - 1),
+// weights PQ K, prefetched samples 2 (R + 1), accumulators and addresses ~32
+constexpr int rsv_min_ctas(int K, int R, int PQ) {
+    const int need = 2 * (R + K - 1) + PQ * K + 2 * (R + 1) + 32;
+    return need <= 96 ? 5 : need <= 128 ? 4 : 3;
+}
 
 // host-side launch geometry of the vector kernel for a group (D, K) at decimated length M; false: not eligible
-// (odd D or K, or a tap count / precision the vector kernels are not compiled for - the scalar kernel takes those)
-struct ResampleVecShape { int R, PQ, nthr, C; unsigned tiles; size_t smem; fastdiv dRD; };
+// (odd D or K, or a tap count / precision the vector kernels are not compiled for - the scalar kernel takes those).
+// R, WR, WP: the most evenly shared phase groups first, then longer runs, then the smaller staging tile (<= 66 KB).
+struct ResampleVecShape { int R, PQ, WR, WP, nthr, C, ctas_per_sm; unsigned items; size_t smem, gbytes; fastdiv dRD; };
 template <typename T> inline bool resample_vec_shape(int D, int K, long long M, ResampleVecShape& v) {
     if (sizeof(T) != 4 || (D & 1) || (K & 1) || K < 4 || K > 12) return false;
-    v.R = resample_vec_run(D);
     v.PQ = (D & 3) ? 2 : 4;
     v.nthr = 128;
-    v.C = v.nthr * v.R;
-    v.tiles = (unsigned)((M + v.C - 1) / v.C);
-    const size_t ys = ((size_t)v.C + K + ((size_t)v.C + K) / v.R + 2) * 2 * sizeof(T);
-    const size_t tile = (size_t)v.nthr * ((size_t)v.R * D + v.PQ) * sizeof(T);
-    v.smem = ys > tile ? ys : tile;
+    const int G = D / v.PQ;
+    double best = -1;
+    static const int RR[2] = {8, 4}, WW[3][2] = {{4, 1}, {2, 2}, {1, 4}};
+    static const double RF[2] = {1.0, 0.95};   // runs of 4: more window and weight loads per output (runs of 16 spill)
+    for (int ri = 0; ri < 2; ++ri)
+        for (int wi = 0; wi < 3; ++wi) {
+            const int R = RR[ri], WR = WW[wi][0], WP = WW[wi][1];
+            const size_t tile = (size_t)32 * WR * ((size_t)R * D + v.PQ) * sizeof(T);
+            const int fit = (int)((227 * 1024) / (tile + 1024));
+            if (fit < 3) continue;
+            const double eff = (double)G / (double)(((G + WP - 1) / WP) * WP);   // phase groups shared evenly by the phase-warps
+            const int rc = rsv_min_ctas(K, R, v.PQ);
+            const double occ = (double)(fit < rc ? fit : rc) / 5.0;                 // resident CTAs: shared memory, registers
+            const double score = eff * occ * RF[ri] - 0.01 * (WP - 1);
+            if (score > best + 1e-9) { best = score; v.R = R; v.WR = WR; v.WP = WP; }
+        }
+    if (best < 0) return false;
+    v.C = 32 * v.WR * v.R;
+    const size_t CG = (size_t)32 * v.R;
+    v.items = (unsigned)((M + (long long)CG - 1) / (long long)CG);
+    const size_t ys = (CG + K + (CG + K) / v.R + 2) * 2 * sizeof(T);
+    const size_t tile = (size_t)32 * ((size_t)v.R * D + v.PQ) * sizeof(T);
+    v.gbytes = ((ys > tile ? ys : tile) + 15) / 16 * 16;
+    v.smem = v.gbytes * v.WR;
+    const int fit = (int)((227 * 1024) / (v.smem + 1024));
+    const int rc = rsv_min_ctas(K, v.R, v.PQ);
+    v.ctas_per_sm = fit < rc ? fit : rc;
     v.dRD = make_fastdiv((uint32_t)(v.R * D / v.PQ));
     return true;
+}
+// persistent grid of the vector kernel for `rows` rows on a device with `sms` SMs
+inline unsigned resample_vec_grid(const ResampleVecShape& v, long long rows, int sms) {
+    const long long ctas = ((long long)v.items * rows + v.WR - 1) / v.WR;
+    const long long cap = (long long)sms * v.ctas_per_sm;
+    return (unsigned)(ctas < cap ? ctas : cap);
 }
 // weights regrouped for the vector kernel: coefq[(p / PQ) K + t][p % PQ] = coef[p][t]
 template <typename T> inline void resample_coefq(const double* coef, int D, int K, int PQ, T* q) {

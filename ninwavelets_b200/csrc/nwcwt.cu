@@ -112,6 +112,8 @@ struct nwcwt_plan {
     size_t l2_window_bytes = 0;
     void* d_rec = nullptr;
     void* d_table = nullptr;
+    void* d_wtab = nullptr;                         // weight table of the bands (nw_plan.h: build_weight_table)
+    const std::vector<double>* eq_host = nullptr;   // sub-plan of a resampled group: the group's equaliser, folded into d_wtab
     // host-call resources
     void* h_in_dev[2] = {nullptr, nullptr};
     void* h_out_dev[2] = {nullptr, nullptr};
@@ -247,6 +249,13 @@ static int ensure_device_t(nwcwt_plan* pl) {
             if ((rc = upload_tw<T>(&pl->d_twB2, hp.N2f, hp.N2f, 1))) return rc;
         }
     }
+    if (hp.path == 1 && hp.fast && !getenv("NWCWT_NO_WTAB")) {
+        std::vector<T> tab;
+        if (build_weight_table<T>(hp, pl->eq_host ? pl->eq_host->data() : nullptr, (size_t)512 << 20, tab)) {
+            CUDA_TRY(cudaMalloc(&pl->d_wtab, tab.size() * sizeof(T)));
+            CUDA_TRY(cudaMemcpy(pl->d_wtab, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice));
+        }
+    }
     if (hp.F > 0) {
         CUDA_TRY(cudaMalloc(&pl->d_rec, sizeof(FreqRec) * hp.F));
         CUDA_TRY(cudaMemcpy(pl->d_rec, hp.rec.data(), sizeof(FreqRec) * hp.F, cudaMemcpyHostToDevice));
@@ -298,6 +307,7 @@ static int ensure_device_t(nwcwt_plan* pl) {
     for (size_t gi = 0; gi < pl->groups.size(); ++gi) {
         nwcwt_plan::Group& g = pl->groups[gi];
         const MrGroup& mg = hp.groups[gi];
+        if (mg.D > 1) g.sub->eq_host = &mg.eq;
         if ((rc = ensure_device_t<T>(g.sub))) return rc;
         CUDA_TRY(cudaMalloc((void**)&g.d_fmap, sizeof(int) * mg.fidx.size()));
         CUDA_TRY(cudaMemcpy(g.d_fmap, mg.fidx.data(), sizeof(int) * mg.fidx.size(), cudaMemcpyHostToDevice));
@@ -347,6 +357,7 @@ static SpecParams<T> make_spec(const nwcwt_plan* pl) {
     sp.rec = (const FreqRec*)pl->d_rec;
     sp.table = (const cx<T>*)pl->d_table;
     sp.table_len = hp.table_len;
+    sp.wtab = (const T*)pl->d_wtab;
     return sp;
 }
 
@@ -551,7 +562,8 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
         R.WR = shp.WR;
         R.WP = shp.WP;
         R.RS = shp.RS;
-        R.dRD = vec ? vshp.dRD : make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
+        R.dRD = make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
+        if (vec) { R.WR = vshp.WR; R.WP = vshp.WP; R.RS = (int)vshp.gbytes; R.dRD = vshp.dRD; R.dGT = make_fastdiv(vshp.items); R.dGT.d = vshp.items; }
         R.coefq = (const T*)dg->d_coefq;
         Q.eq = (const T*)dg->d_eq;
         Q.out_mode = NWCWT_OUT_CWT;
@@ -579,7 +591,8 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
             R.row0 = (int)r0;
             const unsigned tiles = (unsigned)((eh.N + shp.C - 1) / shp.C);
             LaunchScope ls(6, st);
-            if (vec) CUDA_TRY(RsVecDispatch<T>::run(vshp.PQ, output, mg->K, vshp.R, R, dim3(vshp.tiles, g), vshp.smem, st));
+            R.nrows = g;
+            if (vec) CUDA_TRY(RsVecDispatch<T>::run(vshp.PQ, output, mg->K, vshp.R, R, dim3(resample_vec_grid(vshp, g, device_sms(hp.device))), vshp.smem, st));
             else CUDA_TRY(launch_resample<T>(mg->K, output, R, dim3(tiles, g), 32 * shp.WR * shp.WP, shp.smem, st));
         }
     }
@@ -819,7 +832,7 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
     pl->groups.clear();
     if (pl->on_device || pl->h_stream[0]) {
         cudaSetDevice(pl->hp.device);
-        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_twA2, pl->d_twB2,
+        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_wtab, pl->d_twA2, pl->d_twB2,
                         pl->h_in_dev[0], pl->h_in_dev[1], pl->h_out_dev[0], pl->h_out_dev[1], pl->h_ws[0], pl->h_ws[1]};
         for (void* p : ptrs)
             if (p) cudaFree(p);

@@ -89,6 +89,7 @@ static SpecParams<T> make_sp(const HostPlan& hp, const std::vector<cx<T>>& table
     sp.p2 = hp.family == FAM_MORSE ? hp.p0 / hp.p1 : hp.p2;
     sp.norm = (T)(1.0 / (double)hp.data_len());
     sp.rec = hp.rec.data(); sp.table = table.data(); sp.table_len = hp.table_len;
+    sp.wtab = nullptr;
     return sp;
 }
 template <typename T>
@@ -109,12 +110,14 @@ static void resample_launch(const ResampleParams<T>& R, int mode, char* smp, int
 }
 
 template <typename T, int K, int PQ>
-static void resample_vec_launch(const ResampleParams<T>& R, int mode, char* smp, const ResampleVecShape& v, int g) {
-    for (int y = 0; y < g; ++y) for (int x = 0; x < (int)v.tiles; ++x)
+static void resample_vec_launch(ResampleParams<T> R, int mode, char* smp, const ResampleVecShape& v, int g) {
+    R.nrows = g;
+    const int nbx = (int)std::min<unsigned>(resample_vec_grid(v, g, 1), 3u);   // a small persistent grid: every CTA loops
+    for (int x = 0; x < nbx; ++x)
         Fibers::get().run(v.nthr, [&](int t) {
-#define RV(r) case r: if (mode == OUT_POWER) resample_vec_body<T, K, r, PQ, OUT_POWER>(R, smp, x, y, t, v.nthr); \
-                      else resample_vec_body<T, K, r, PQ, OUT_ABS>(R, smp, x, y, t, v.nthr); break;
-            switch (v.R) { RV(16) RV(8) RV(4) RV(2) }
+#define RV(r) case r: if (mode == OUT_POWER) resample_vec_body<T, K, r, PQ, OUT_POWER>(R, smp, x, nbx, t, v.nthr); \
+                      else resample_vec_body<T, K, r, PQ, OUT_ABS>(R, smp, x, nbx, t, v.nthr); break;
+            switch (v.R) { RV(8) RV(4) }
 #undef RV
         });
 }
@@ -122,7 +125,10 @@ static void resample_vec_launch(const ResampleParams<T>& R, int mode, char* smp,
 // Inverse transforms of gs signals x the frequencies of plan eh (the main plan, or the sub-plan of group mg) on the
 // packed kernels, followed by the interpolation kernel for a resampled group: mirrors nwcwt.cu: inverse_rows.
 template <typename T>
-static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* mg, const cx<T>* X, void* out_s0, int gs, int output) {
+static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup* mg, const cx<T>* X, void* out_s0, int gs, int output) {
+    HostPlan eh = eh_in;   // the weight table sets FreqRec::woff
+    std::vector<T> wtab;
+    const bool have_wtab = !(g_mode & 256) && build_weight_table<T>(eh, mg && mg->D > 1 ? mg->eq.data() : nullptr, (size_t)512 << 20, wtab);
     std::vector<cx<T>> table, twA2, twB2, twH, twL;
     make_table<T>(eh, table);
     fill_tw<T>(twA2, eh.N1f, eh.N1f, 1);
@@ -136,6 +142,7 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* m
     Q.N = eh.N; Q.xstride = hp.N; Q.N1 = eh.N1f; Q.N2 = eh.N2f; Q.F = eh.F; Q.tpshA = eh.tpshA; Q.tpshB = eh.tpshB;
     Q.stA = eh.stA2; Q.stB = eh.stB2; Q.twA = twA2.data(); Q.twB = twB2.data(); Q.twH = twH.data(); Q.twL = twL.data();
     Q.lb = eh.lb; Q.tm_stride = eh.tm_stride2; Q.sp = make_sp<T>(eh, table);
+    if (have_wtab) Q.sp.wtab = wtab.data();
     const int ring2 = eh.ring2 < 3 ? eh.ring2 : 3;
     std::vector<cx<T>> Tm2((size_t)ring2 * eh.tm_stride2), Y;
     Q.X = X; Q.Tm = Tm2.data();
@@ -160,7 +167,7 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh, const MrGroup* m
             coefq.resize(coef.size());
             resample_coefq<T>(mg->coef.data(), D, mg->K, vshp.PQ, coefq.data());
             R.coefq = coefq.data();
-            R.dRD = vshp.dRD;
+            R.WR = vshp.WR; R.WP = vshp.WP; R.RS = (int)vshp.gbytes; R.dRD = vshp.dRD; R.dGT = make_fastdiv(vshp.items); R.dGT.d = vshp.items;
         }
         Q.eq = eq.data();
         Q.out_mode = OUT_CWT;
