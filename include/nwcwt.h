@@ -32,7 +32,7 @@ extern "C" {
 enum nwcwt_error {
     NWCWT_OK = 0,
     NWCWT_ERR_INVALID = -1,     /* bad argument */
-    NWCWT_ERR_UNSUPPORTED = -2, /* signal length with a prime factor the engine cannot take */
+    NWCWT_ERR_UNSUPPORTED = -2, /* a request outside what the library implements (message has the detail) */
     NWCWT_ERR_CUDA = -3,        /* CUDA runtime error (message has the detail) */
     NWCWT_ERR_WORKSPACE = -4,   /* workspace too small */
     NWCWT_ERR_ZERO_FREQ = -5    /* freq == 0: base.py:234-235 raises ZeroDivisionError */
@@ -102,7 +102,9 @@ typedef struct nwcwt_plan_info {
     int32_t n_freqs;
     int32_t path;          /* 0 = short rows (one CTA per signal), 1 = long rows (two passes, generic
                               kernels), 2 = long rows (two passes, packed in-place kernels), 3 = short rows
-                              (packed in-place kernel, one CTA per signal pair) */
+                              (packed in-place kernel, one CTA per signal pair), 4 = any length whose radix plan
+                              does not exist (a prime factor > 64): Bluestein's chirp-z algorithm on transforms of
+                              the smooth length n1 >= 2 n - 1 */
     int32_t n1, n2;        /* long rows: n = n1 * n2 */
     int32_t batch;         /* frequencies (short) / columns (long) interleaved per CTA */
     int32_t n_stages[2];   /* radix stages of the n (short) or n1, n2 (long) point transforms */
@@ -129,6 +131,10 @@ int64_t nwcwt_launch_count(void);
  * pass B, [3] inverse pass A, [4] inverse pass B, [5] baseline rows / epoch reductions, [6] interpolation of
  * resampled rows, [7] reserved, and resets them. */
 int nwcwt_profile_enable(int32_t on);
+/* Measured rate of the FP32 (dtype F32: packed FFMA2 chains) or FP64 (DFMA chains) pipe of `device`, in lane
+ * multiply-adds per second: the denominator of bench.py's FLOP roofline (SURVEY.md 8d asks for the HBM and the
+ * FLOP fraction of every config). */
+int nwcwt_fma_peak(int32_t device, int32_t dtype, double* lane_ops_per_s);
 /* Test hook: non-zero makes every transform use the generic (any-length) kernels even where the plan has
  * the packed fast path, so both can be checked against the oracle on the same input. */
 int nwcwt_debug_force_generic(int32_t on);
@@ -158,6 +164,15 @@ int nwcwt_spectrum_bank(nwcwt_plan* plan, void* bank_dev, void* stream);
  *   kind 1: inter-trial coherence |mean(z / |z|)| of a complex array in [n_epochs][count] -> real out [count] */
 int nwcwt_reduce_epochs(nwcwt_plan* plan, const void* in_dev, void* out_dev, int64_t n_epochs, int64_t count,
                         int32_t kind, void* stream);
+
+/* Epoch reductions FUSED into the transform (mneutils.py:42-55, 57-71): signals_dev [n_channels][n_epochs][n] real;
+ *   kind 0: out_dev [n_channels][n_freqs][n] = mean over epochs of |cwt|^2
+ *   kind 1: out_dev [n_channels][n_freqs][n] = |mean over epochs of cwt / |cwt||   (inter-trial coherence)
+ * The (n_epochs, n_freqs, n) array of per-epoch rows is never materialised: a CTA loops over the epochs of its channel
+ * and accumulates into the result.  kind 1 needs a workspace of n_channels * n_freqs * n complex values.  Rows must fit
+ * one CTA (plan path 3); otherwise NWCWT_ERR_UNSUPPORTED - use nwcwt_transform + nwcwt_reduce_epochs. */
+int nwcwt_transform_epochs(nwcwt_plan* plan, const void* signals_dev, void* out_dev, int64_t n_channels, int64_t n_epochs,
+                           int32_t kind, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Baseline (base.py:46-68) applied in place to n_rows rows of length n (dtype real): the standalone
  * form of the epilogue, for `Baseline(wave, sfreq, start, stop).<mode>()` on data already on the device. */

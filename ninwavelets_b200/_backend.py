@@ -61,7 +61,7 @@ SYMBOLS = (
     "nwcwt_plan_get_bands", "nwcwt_workspace_bytes", "nwcwt_spectrum_bank", "nwcwt_reduce_epochs",
     "nwcwt_baseline_rows", "nwcwt_launch_count", "nwcwt_profile_enable", "nwcwt_profile_read",
     "nwcwt_forward", "nwcwt_transform", "nwcwt_transform_host", "nwcwt_debug_force_generic",
-    "nwcwt_debug_force_exact",
+    "nwcwt_debug_force_exact", "nwcwt_fma_peak", "nwcwt_transform_epochs",
 )
 
 
@@ -86,6 +86,7 @@ def lib():
             L.nwcwt_spectrum_bank.argtypes = [vp, vp, vp]
             L.nwcwt_reduce_epochs.argtypes = [vp, vp, vp, i64, i64, i32, vp]
             L.nwcwt_forward.argtypes = [vp, vp, vp, i64, vp, sz, vp]
+            L.nwcwt_transform_epochs.argtypes = [vp, vp, vp, i64, i64, i32, vp, sz, vp]
             L.nwcwt_transform.argtypes = [vp, vp, vp, i64, i32, i32, i64, i64, vp, sz, vp]
             L.nwcwt_transform_host.argtypes = [vp, vp, vp, i64, i32, i32, i64, i64]
             L.nwcwt_launch_count.restype = C.c_int64
@@ -124,6 +125,15 @@ def force_generic(on):
     _check(lib().nwcwt_debug_force_generic(C.c_int32(1 if on else 0)))
 
 
+def fma_peak(device, f32=True):
+    """Measured FP32 (FFMA2) / FP64 (DFMA) pipe rate of the device in lane multiply-adds per second."""
+    v = C.c_double()
+    L = lib()
+    L.nwcwt_fma_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    _check(L.nwcwt_fma_peak(int(device), F32 if f32 else F64, C.byref(v)))
+    return float(v.value)
+
+
 def profile_enable(on):
     _check(lib().nwcwt_profile_enable(int(bool(on))))
 
@@ -140,7 +150,10 @@ def _dptr(a):
 
 
 class Plan:
-    """Device-side counterpart of `WaveletBase.fft_wavelets` for one (family, freqs, N, dtype)."""
+    """Device-side counterpart of `WaveletBase.fft_wavelets` for one (family, freqs, N, dtype).
+
+    A plan owns one workspace and one set of auxiliary streams: use it from one thread and one CUDA stream
+    at a time (build one plan per concurrent stream)."""
 
     def __init__(self, *, device, dtype, family, interpolate, n, sfreq, freqs, p0=0.0, p1=0.0, p2=0.0,
                  aux=None, table=None, table_lens=None, prune_eps=-1.0, resample=None, resample_tol=0.0):
@@ -164,7 +177,8 @@ class Plan:
             keep.append(aux)
         if table is not None:
             table = np.ascontiguousarray(np.asarray(table, dtype=np.complex128))
-            assert table.ndim == 2 and table.shape[0] == self.n_freqs
+            if table.ndim != 2 or table.shape[0] != self.n_freqs:
+                raise ValueError("table must be [n_freqs, table_len]")
             d.table = table.view(np.float64).ctypes.data_as(C.POINTER(C.c_double))
             d.table_len = table.shape[1]
             keep.append(table)
@@ -183,7 +197,7 @@ class Plan:
     def info(self):
         i = PlanInfo()
         _check(lib().nwcwt_plan_get_info(self._h, C.byref(i)))
-        out = dict(n=i.n, n_freqs=i.n_freqs, path=("short", "long", "long_packed", "short_packed")[i.path], n1=i.n1, n2=i.n2,
+        out = dict(n=i.n, n_freqs=i.n_freqs, path=("short", "long", "long_packed", "short_packed", "chirp_z")[i.path], n1=i.n1, n2=i.n2,
                    batch=i.batch, band_bins=i.band_bins, smem_bytes=i.smem_bytes, threads=list(i.threads),
                    rows_per_launch=i.rows_per_launch)
         out["radices"] = [list(i.radices[k][: i.n_stages[k]]) for k in range(2)]
@@ -218,6 +232,11 @@ class Plan:
             self._ws = torch.empty(need, dtype=torch.uint8, device="cuda:%d" % self.device)
         return self._ws, need
 
+    def _check_device_tensor(self, t, name):
+        """A plan works on its own device only (its tables and workspace live there)."""
+        if not t.is_cuda or t.device.index != self.device:
+            raise ValueError("%s must be a CUDA tensor on the plan's device cuda:%d, got %s" % (name, self.device, t.device))
+
     def _tdtype(self, torch, complex_=False):
         if self.dtype == F64:
             return torch.complex128 if complex_ else torch.float64
@@ -226,14 +245,20 @@ class Plan:
     def transform_device(self, signals, output=OUT_POWER, baseline=0, base_lo=0, base_hi=0, out=None):
         """signals: torch CUDA tensor [S, N] of the plan's real dtype -> torch tensor [S, F, N]."""
         torch = self._torch()
-        assert signals.is_cuda and signals.dim() == 2 and signals.shape[1] == self.n
+        self._check_device_tensor(signals, "signals")
+        if signals.dim() != 2 or signals.shape[1] != self.n:
+            raise ValueError("signals must be [n_signals, %d], got %s" % (self.n, tuple(signals.shape)))
         signals = signals.contiguous()
         if signals.dtype != self._tdtype(torch):
             signals = signals.to(self._tdtype(torch))
         S = signals.shape[0]
+        odt = self._tdtype(torch, output == OUT_CWT)
         if out is None:
-            out = torch.empty((S, self.n_freqs, self.n), dtype=self._tdtype(torch, output == OUT_CWT),
-                              device=signals.device)
+            out = torch.empty((S, self.n_freqs, self.n), dtype=odt, device=signals.device)
+        else:
+            self._check_device_tensor(out, "out")
+            if tuple(out.shape) != (S, self.n_freqs, self.n) or out.dtype != odt or not out.is_contiguous():
+                raise ValueError("out must be a contiguous %s tensor of shape %s" % (odt, (S, self.n_freqs, self.n)))
         ws, need = self._workspace(torch, S)
         stream = torch.cuda.current_stream(signals.device).cuda_stream
         _check(lib().nwcwt_transform(self._h, signals.data_ptr(), out.data_ptr(), S, int(output), int(baseline),
@@ -243,6 +268,9 @@ class Plan:
 
     def forward_device(self, signals):
         torch = self._torch()
+        self._check_device_tensor(signals, "signals")
+        if signals.dim() != 2 or signals.shape[1] != self.n:
+            raise ValueError("signals must be [n_signals, %d], got %s" % (self.n, tuple(signals.shape)))
         signals = signals.contiguous().to(self._tdtype(torch))
         S = signals.shape[0]
         spec = torch.empty((S, self.n), dtype=self._tdtype(torch, True), device=signals.device)
@@ -269,11 +297,32 @@ class Plan:
         _check(lib().nwcwt_reduce_epochs(self._h, x.data_ptr(), out.data_ptr(), E, out.numel(), int(kind), stream))
         return out
 
+    def transform_epochs_device(self, signals, kind):
+        """signals: torch CUDA tensor [C, E, N] -> [C, F, N] real: mean power over epochs (kind 0) or inter-trial
+        coherence (kind 1), reduced inside the transform kernel.  Raises BackendError(ERR_UNSUPPORTED) for rows that
+        do not fit one CTA (callers fall back to transform_device + reduce_epochs_device)."""
+        torch = self._torch()
+        self._check_device_tensor(signals, "signals")
+        if signals.dim() != 3 or signals.shape[2] != self.n:
+            raise ValueError("signals must be [n_channels, n_epochs, %d], got %s" % (self.n, tuple(signals.shape)))
+        signals = signals.contiguous().to(self._tdtype(torch))
+        Cn, E = int(signals.shape[0]), int(signals.shape[1])
+        out = torch.empty((Cn, self.n_freqs, self.n), dtype=self._tdtype(torch), device=signals.device)
+        ws = None
+        if kind == 1:
+            ws = torch.empty((Cn, self.n_freqs, self.n), dtype=self._tdtype(torch, True), device=signals.device)
+        stream = torch.cuda.current_stream(signals.device).cuda_stream
+        _check(lib().nwcwt_transform_epochs(self._h, signals.data_ptr(), out.data_ptr(), Cn, E, int(kind),
+                                            ws.data_ptr() if ws is not None else None,
+                                            ws.numel() * ws.element_size() if ws is not None else 0, stream))
+        return out
+
     def transform_host(self, signals, output=OUT_POWER, baseline=0, base_lo=0, base_hi=0, out=None, pinned=True):
         """signals: numpy [S, N] -> numpy [S, F, N]; copies are inside the call (pinned result buffer)."""
         torch = self._torch()
         signals = np.ascontiguousarray(signals, dtype=self.real_dtype)
-        assert signals.ndim == 2 and signals.shape[1] == self.n
+        if signals.ndim != 2 or signals.shape[1] != self.n:
+            raise ValueError("signals must be [n_signals, %d], got %s" % (self.n, signals.shape))
         S = signals.shape[0]
         odt = self.cplx_dtype if output == OUT_CWT else self.real_dtype
         if out is None:
@@ -283,7 +332,8 @@ class Plan:
                 out = holder.numpy()
             else:
                 out = np.empty((S, self.n_freqs, self.n), dtype=odt)
-        assert out.dtype == odt and out.flags.c_contiguous
+        if out.dtype != odt or not out.flags.c_contiguous or out.shape != (S, self.n_freqs, self.n):
+            raise ValueError("out must be a C-contiguous %s array of shape %s" % (odt, (S, self.n_freqs, self.n)))
         _check(lib().nwcwt_transform_host(self._h, signals.ctypes.data, out.ctypes.data, S, int(output),
                                           int(baseline), int(base_lo), int(base_hi)))
         return out

@@ -11,6 +11,11 @@ Extensions (keyword-only, all default to the reference's behaviour):
   dtype      'float64' (reference precision) or 'float32' (the fast mode)
   device     CUDA ordinal (default: current torch device)
   prune_eps  spectrum bins below prune_eps * peak are skipped (None: library default)
+  resample   long rows, abs / power: None or True lets the library compute band-limited rows at a
+             decimated length and interpolate them ("resampled rows"); False forces the
+             exact length-N inverse transform for every row
+  resample_tol  bound on the interpolation error of a resampled row relative to the wavelet's peak
+             gain times the input's spectral mass (0: library default, 1e-6 in float32, 5e-14 in float64)
 and `wave` may be a 2-D `[S, N]` batch or a torch CUDA tensor (then the result
 stays on the device).
 """
@@ -122,7 +127,8 @@ class WaveletBase:
 
     def __init__(self, sfreq: float = 1000, real_wave_length: float = 1., interpolate: bool = True,
                  cuda: bool = False, *, dtype="float64", device: Optional[int] = None,
-                 prune_eps: Optional[float] = None) -> None:
+                 prune_eps: Optional[float] = None, resample: Optional[bool] = None,
+                 resample_tol: float = 0.0) -> None:
         self.mode: WaveletMode = WaveletMode.Normal
         self.sfreq: float = sfreq
         self.help: str = ''
@@ -135,6 +141,8 @@ class WaveletBase:
             raise ValueError("dtype must be float32 or float64")
         self.device = device
         self.prune_eps = prune_eps
+        self.resample = resample
+        self.resample_tol = resample_tol
         self._plan: Optional[_be.Plan] = None
 
     # ---- formulas a family may override (reference base.py:218-219, 281-344) ---
@@ -195,6 +203,11 @@ class WaveletBase:
                 "%s(cuda=False): ninwavelets_b200 implements only the device path of the reference "
                 "(cuda=True); it has no numpy/scipy fallback" % type(self).__name__)
 
+    def _uses_native(self) -> bool:
+        """The family's spectrum is one of the built-in analytic formulas (real valued), evaluated by the device."""
+        return self.mode in (WaveletMode.Reverse, WaveletMode.Both) and self._native is not None \
+            and not self._is_overridden("trans_formula") and not self._is_overridden("peak_freq")
+
     def _is_overridden(self, name: str) -> bool:
         """True if a user subclass replaced a formula of a built-in family."""
         for klass in type(self).__mro__:
@@ -204,7 +217,7 @@ class WaveletBase:
 
     def _normal_mode_tables(self, freqs):
         """Spectra of time-domain families (reference base.py:250-255): wavelet, symmetric zero
-        padding to sfreq*real_wave_length samples, forward FFT (on the device, fp64), |re| + i|im|."""
+        padding to sfreq*real_wave_length samples, forward FFT, |re| + i|im|."""
         rows = []
         for f in freqs:
             if f == 0:
@@ -214,16 +227,11 @@ class WaveletBase:
             rows.append(np.hstack((np.zeros(half), w, np.zeros(half))))
         lens = np.array([r.shape[0] for r in rows], dtype=np.int64)
         table = np.zeros((len(rows), int(lens.max())), dtype=np.complex128)
-        import torch
-        dev = self._device_index()
-        for m in np.unique(lens):
-            idx = np.nonzero(lens == m)[0]
-            fplan = _be.Plan(device=dev, dtype=np.float64, family=_be.SHANNON, interpolate=False, n=int(m),
-                             sfreq=self.sfreq, freqs=[])
-            x = torch.as_tensor(np.stack([rows[i] for i in idx]), device="cuda:%d" % dev)
-            spec = fplan.forward_device(x).cpu().numpy()
-            table[idx, :m] = np.abs(spec.real) + 1j * np.abs(spec.imag)
-            fplan.close()
+        # plan-time precomputation of F short tables (sfreq * real_wave_length samples each), done on the host like
+        # the reference does (base.py:253) so that it works for every table length
+        for i, r in enumerate(rows):
+            spec = np.fft.fft(r)
+            table[i, :lens[i]] = np.abs(spec.real) + 1j * np.abs(spec.imag)
         return table, lens
 
     def _build_plan(self, freqs, n: int) -> "_be.Plan":
@@ -231,10 +239,10 @@ class WaveletBase:
         if np.any(freqs_arr == 0):
             raise ZeroDivisionError  # reference base.py:234-235
         common = dict(device=self._device_index(), dtype=self.dtype, interpolate=self.interpolate, n=n,
-                      sfreq=self.sfreq, freqs=freqs_arr, prune_eps=self.prune_eps)
+                      sfreq=self.sfreq, freqs=freqs_arr, prune_eps=self.prune_eps, resample=self.resample,
+                      resample_tol=self.resample_tol)
         analytic = self.mode in (WaveletMode.Reverse, WaveletMode.Both)
-        if analytic and self._native is not None and not self._is_overridden("trans_formula") \
-                and not self._is_overridden("peak_freq"):
+        if self._uses_native():
             return _be.Plan(**common, **self._native(freqs_arr))
         if analytic:
             # user-supplied numpy trans_formula: tabulate it on the reference's grid (base.py:239-246)
@@ -265,7 +273,7 @@ class WaveletBase:
         plan = self._build_plan([freq], n)
         bank = plan.spectrum_bank_device().cpu().numpy().astype(np.complex128)[0]
         plan.close()
-        return bank.real.copy() if self.mode in (WaveletMode.Reverse, WaveletMode.Both) else bank
+        return bank.real.copy() if self._uses_native() else bank   # tabulated (user / Normal-mode) spectra may be complex
 
     def make_fft_wavelets(self, freqs: Numbers, real_wave_length: float = 1.):
         """Build the plan that replaces the spectrum cache (reference base.py:258-279)."""
@@ -273,21 +281,21 @@ class WaveletBase:
         self.freq_dist = freqs[1] - freqs[0]   # IndexError / TypeError like the reference (base.py:272)
         n = int(round(real_wave_length * self.sfreq))
         self._plan = self._build_plan(freqs, n)
-        self.fft_wavelets = _LazyBank(self._plan, self.mode in (WaveletMode.Reverse, WaveletMode.Both))
+        self.fft_wavelets = _LazyBank(self._plan, self._uses_native())
         return self.fft_wavelets
 
     def _plan_for(self, n: int, freqs, reuse: bool) -> "_be.Plan":
         if (not reuse) or (not hasattr(self, 'fft_wavelets')):
             self.freq_dist = freqs[1] - freqs[0]
             self._plan = self._build_plan(freqs, n)
-            self.fft_wavelets = _LazyBank(self._plan, self.mode in (WaveletMode.Reverse, WaveletMode.Both))
+            self.fft_wavelets = _LazyBank(self._plan, self._uses_native())
         elif self._plan.n != n:
             # reference quirk (base.py:396-397): a cached bank built for another length is
             # pad_to'ed (truncated / centre padded) onto the new signal
             old = np.asarray(self.fft_wavelets._materialise(), dtype=np.complex128)
             self._plan = _be.Plan(device=self._device_index(), dtype=self.dtype, interpolate=self.interpolate,
                                   n=n, sfreq=self.sfreq, freqs=self._plan.freqs, family=_be.TABLE, table=old,
-                                  prune_eps=self.prune_eps)
+                                  prune_eps=self.prune_eps, resample=self.resample, resample_tol=self.resample_tol)
         return self._plan
 
     # ---- transforms (reference base.py:378-443) -------------------------------------------

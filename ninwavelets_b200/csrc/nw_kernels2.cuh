@@ -44,6 +44,7 @@ struct Long2Params {
     // (signed) transform bin j - applied to the spectrum so that the interpolated row is exact in the pass band
     const T* eq;
     int narrow;         // launch the narrow-band variant of pass A (host side only)
+    const int* ditpos;  // [N1] fft2_dit_pos(stA, k1) tabulated (nullptr: computed per element)
     fastdiv dstepA;     // narrow-band pass A: x / (N1 / radix of the first pass)
     int row0;           // first row (signal-major: row = signal * F + frequency) of this launch
     int out_mode;
@@ -239,9 +240,11 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         for (int i = tid; i < (N1 << tpsh); i += nthr) {
             const int tp = i & (TP - 1);
             const int k1 = i >> tpsh;
-            int u = (k1 - k1lo) % N1;
+            int u = k1 - k1lo;             // |k1lo| <= N1: u in (-N1, 2 N1)
             if (u < 0) u += N1;
-            buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1lo + u, c + 2 * tp);
+            if (u >= N1) u -= N1;
+            const int pos = P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
+            buf[((size_t)pos << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1lo + u, c + 2 * tp);
         }
         NW_SYNC();
         if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
@@ -256,7 +259,8 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         const int k1s = k1lo + (i >> tpsh);
         int k1 = k1s % N1;
         if (k1 < 0) k1 += N1;
-        buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1s, c + 2 * tp);
+        const int pos = P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
+        buf[((size_t)pos << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1s, c + 2 * tp);
     }
     NW_SYNC();
     if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);

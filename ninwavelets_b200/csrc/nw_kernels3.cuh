@@ -30,6 +30,10 @@ struct Short2Params {
     Fft2Plan st;
     const cx<T>* tw;    // [N]
     SpecParams<T> sp;
+    // epoch reductions (short2_epochs_body): signals are [n_channels][n_epochs][N]; acc is the complex accumulator of
+    // the inter-trial coherence, [n_channels][F][N]
+    int n_epochs;
+    cx<T>* acc;
 };
 
 template <typename T> NW_HD size_t short2_smem_bytes(int N, int tpsh) {
@@ -235,6 +239,89 @@ NW_HD void short2_body(const Short2Params<T>& P, char* smem, int bx, int tid, in
             }
         }
         NW_SYNC();
+    }
+}
+
+// ---- epoch reductions fused into the transform (mneutils.py:53-55 mean power over epochs, :68-71 inter-trial coherence) --
+// One CTA owns a CHANNEL and a share of the frequency groups and loops over the channel's epochs two at a time (the two
+// lanes): forward transform of the epoch pair, then for each of its frequency groups the inverse transform as in
+// short2_body, whose rows are not written out but accumulated into the channel's (F, N) result - every (frequency, sample)
+// of it is owned by exactly one thread of one CTA, so the accumulation is a plain read-add-write of L2-resident lines and
+// the (E, F, N) array of per-epoch rows is never materialised.
+//   KIND 0: out[c][f][n] = mean_e |z_e|^2        KIND 1: out[c][f][n] = | mean_e z_e / |z_e| |  (complex sums in P.acc)
+template <typename T, int KIND, int SP>
+NW_HD void short2_epochs_body(const Short2Params<T>& P, char* smem, int bx, int tid, int nthr) {
+    const int N = P.N, tpsh = P.tpsh, NF = 1 << tpsh, E = P.n_epochs;
+    cx2<T>* Xs = (cx2<T>*)smem;
+    cx2<T>* buf = Xs + N;
+    const int ch = bx / P.fsplit, part = bx - ch * P.fsplit;
+    typedef StaticPlan<SP> SPL;
+    const int ngroups = (P.F + NF - 1) >> tpsh;
+    const cx2<T> z = zero2<T>();
+    const T inv_e = (T)1 / (T)E;
+    constexpr int MODE = KIND == 0 ? OUT_POWER : OUT_CWT;
+    for (int i = tid; i < (N << tpsh); i += nthr) buf[i] = z;
+    for (int e0 = 0; e0 < E; e0 += 2) {
+        const bool has1 = e0 + 1 < E, first = e0 == 0, last = e0 + 2 >= E;
+        NW_SYNC();   // the previous pair's rows are consumed (and the tile is zero) before Xs is overwritten
+        {
+            const T* x0 = P.signals + ((size_t)ch * E + e0) * (size_t)N;
+            RealPairSrc<T> src{x0, has1 ? x0 + N : x0};
+            SpectrumPairDst<T> dst{Xs};
+            fft2_dit<T, -1>(P.st, 0, P.tw, buf, src, dst, tid, nthr);   // first pass reads global memory, writes buf slots it later re-reads
+        }
+        NW_SYNC();
+        // the forward transform used the tile as its work space: zero it again for the gathers
+        for (int i = tid; i < (N << tpsh); i += nthr) buf[i] = z;
+        NW_SYNC();
+        for (int g = part; g < ngroups; g += P.fsplit) {
+            const int f0 = g << tpsh;
+            const int nvalid = (P.F - f0 < NF) ? (P.F - f0) : NF;
+            for (int t = 0; t < nvalid; ++t) {
+                const int fi = f0 + t;
+                const FreqRec rec = P.sp.rec[fi];
+                for (int k = rec.lo + tid; k < rec.hi; k += nthr) {
+                    const cx2<T> x = Xs[k];
+                    cx2<T> y;
+                    if (P.sp.family == FAM_TABLE) {
+                        const cx<T> w = scale(P.sp.table[(long long)fi * P.sp.table_len + (k - rec.toff)], P.sp.norm);
+                        y = cmul_s(x, w);
+                    } else {
+                        const T w = SpecEval<T>::real(P.sp, rec, k);
+                        y = mk2<T>(x.re * w, x.im * w);
+                    }
+                    buf[((size_t)fft2_dit_pos(P.st, k) << tpsh) + t] = y;
+                }
+            }
+            NW_SYNC();
+            InPlaceOutDst<T, MODE> dst{buf, tpsh};
+            if constexpr (SP == 0) fft2_dit<T, +1>(P.st, tpsh, P.tw, buf, FromBuf(), dst, tid, nthr);
+            else fft2_dit_static<T, +1, SPL::TPS, (SP ? SPL::P : 4), (SP ? SPL::R0 : 2), (SP ? SPL::R1 : 2), SPL::R2>(P.tw, buf, dst, tid, nthr);
+            NW_SYNC();
+#pragma unroll 1
+            for (int t = 0; t < nvalid; ++t) {
+                const size_t row = ((size_t)ch * P.F + (f0 + t)) * (size_t)N;
+                for (int n = tid; n < N; n += nthr) {
+                    const cx2<T> v = buf[((size_t)n << tpsh) + t];
+                    buf[((size_t)n << tpsh) + t] = z;   // the next pass gathers into a zero tile
+                    if (KIND == 0) {
+                        T* o = (T*)P.out + row + n;
+                        T a = pk_lo(v.re) + (has1 ? pk_hi(v.re) : (T)0);
+                        if (!first) a += *o;
+                        *o = last ? a * inv_e : a;
+                    } else {
+                        const cx<T> u0 = lane0(v), u1 = lane1(v);
+                        const T r0 = (T)1 / nw_hypot(u0.x, u0.y), r1 = has1 ? (T)1 / nw_hypot(u1.x, u1.y) : (T)0;
+                        cx<T> a = mk<T>(u0.x * r0 + (has1 ? u1.x * r1 : (T)0), u0.y * r0 + (has1 ? u1.y * r1 : (T)0));
+                        cx<T>* ac = P.acc + row + n;
+                        if (!first) a = a + *ac;
+                        if (last) ((T*)P.out)[row + n] = nw_hypot(a.x * inv_e, a.y * inv_e);
+                        else *ac = a;
+                    }
+                }
+            }
+            NW_SYNC();
+        }
     }
 }
 

@@ -31,6 +31,9 @@ template <typename T> cudaError_t prepare_short2();
 template <typename T> bool has_static_short2(int sp);
 template <typename T>
 cudaError_t launch_short2(int sp, const Short2Params<T>& P, unsigned grid, int nthr, size_t smem, cudaStream_t s);
+// the same kernel with the epoch reduction fused in (nw_kernels3.cuh: short2_epochs_body); kind 0 = mean power, 1 = ITC
+template <typename T>
+cudaError_t launch_short2_epochs(int sp, int kind, const Short2Params<T>& P, unsigned grid, int nthr, size_t smem, cudaStream_t s);
 // interpolation kernel of the resampled rows (nw_resample.cuh); K = taps, mode = OUT_ABS / OUT_POWER
 template <typename T> cudaError_t prepare_resample();
 template <typename T> bool has_resample(int K);

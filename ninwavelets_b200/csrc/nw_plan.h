@@ -505,12 +505,20 @@ inline void plan_shape_fast(HostPlan& hp) {
         hp.nthrA2 = cap64(hp.smem_A2, hp.stA2, hp.tpshA);
         hp.nthrB2 = cap64(hp.smem_B2, hp.stB2, hp.tpshB);
     }
-    hp.nthrA2 = env_int("NWCWT_NTHR_A", hp.nthrA2);   // tuning overrides
-    hp.nthrB2 = env_int("NWCWT_NTHR_B", hp.nthrB2);
+    // tuning overrides, validated against what the kernels are compiled for: a launch shape that exists, and a whole
+    // number of warps within the shape's launch bound (fp64: 512, the bound of its single shape)
     if (hp.dtype == 0) {   // launch shapes exist in fp32 only
-        hp.cfgA = env_int("NWCWT_CFG_A", hp.cfgA);
-        hp.cfgB = env_int("NWCWT_CFG_B", hp.cfgB);
+        const int ca = env_int("NWCWT_CFG_A", hp.cfgA), cb = env_int("NWCWT_CFG_B", hp.cfgB);
+        if (ca >= 0 && ca < N_CFG2) hp.cfgA = ca;
+        if (cb >= 0 && cb < N_CFG2) hp.cfgB = cb;
     }
+    auto clamp_thr = [&](int v, int cfg) {
+        const int cap = hp.dtype == 0 ? (cfg == 0 ? 512 : CFG2_MAXTHR[cfg]) : 512;
+        v = (v + 31) / 32 * 32;
+        return v < 32 ? 32 : v > cap ? cap : v;
+    };
+    hp.nthrA2 = clamp_thr(env_int("NWCWT_NTHR_A", hp.nthrA2), hp.cfgA);
+    hp.nthrB2 = clamp_thr(env_int("NWCWT_NTHR_B", hp.nthrB2), hp.cfgB);
     const int TB = 2 << hp.tpshB;
     const long long nblk = (hp.N1f + TB - 1) / TB;
     hp.tm_stride2 = nblk * hp.N2f * TB;
@@ -546,7 +554,10 @@ inline void plan_shape_short2(HostPlan& hp) {
     long long maxnb = 0;
     for (int s = 0; s < st.nst; ++s) maxnb = std::max(maxnb, (long long)(st.P / st.radix[s]) << pick);
     hp.nthrS2 = (int)std::min<long long>(256, std::max<long long>(64, (maxnb + 31) / 32 * 32));
-    hp.nthrS2 = env_int("NWCWT_NTHR_S", hp.nthrS2);
+    {   // tuning override: a whole number of warps, at most the kernel's launch bound
+        int v = (env_int("NWCWT_NTHR_S", hp.nthrS2) + 31) / 32 * 32;
+        hp.nthrS2 = v < 32 ? 32 : v > 256 ? 256 : v;
+    }
 }
 
 inline void plan_multirate(HostPlan& hp);
@@ -703,9 +714,11 @@ inline void kb_response(int D, int K, double beta, long long M, const std::vecto
 // wavelet) x (sum of the input's spectral magnitudes) - the scale the rounding error of the exact fp32 / fp64 transform
 // itself lives on.  Bins whose weight is below resample_tol / 8 are dropped from a resampled row's band.
 
-// alias gain A(j) of the kernel (D, K, beta) at NA + 1 offsets j = i * (M / 2) / NA
+// alias gain A(j) and relative pass-band response Hr(j) = |H(j) / H(0)| of the kernel (D, K, beta) at NA + 1 offsets
+// j = i * (M / 2) / NA
 static const int KB_NA = 64;
-inline void kb_alias_curve(int D, int K, double beta, long long M, std::vector<double>& A) {
+struct KbCurve { std::vector<double> A, Hr; };
+inline void kb_alias_curve(int D, int K, double beta, long long M, KbCurve& c) {
     std::vector<long long> bins;
     bins.reserve((size_t)(KB_NA + 1) * D);
     for (int i = 0; i <= KB_NA; ++i) {
@@ -714,21 +727,24 @@ inline void kb_alias_curve(int D, int K, double beta, long long M, std::vector<d
     }
     std::vector<double> H;
     kb_response(D, K, beta, M, bins, H);
-    A.resize(KB_NA + 1);
+    c.A.resize(KB_NA + 1);
+    c.Hr.resize(KB_NA + 1);
     for (int i = 0; i <= KB_NA; ++i) {
         double al = 0.0;
         for (int r = 1; r < D; ++r) al += H[(size_t)i * D + r] * H[(size_t)i * D + r];
         const double main = fabs(H[(size_t)i * D]);
-        A[(size_t)i] = main > 0 ? sqrt(al) / main : 1e300;
+        c.A[(size_t)i] = main > 0 ? sqrt(al) / main : 1e300;
+        c.Hr[(size_t)i] = fabs(H[0]) > 0 ? main / fabs(H[0]) : 0.0;
     }
 }
-// upper envelope of A on the cell that holds offset |j| (A is smooth on the scale of a cell; ripples span many cells)
-inline double kb_alias_at(const std::vector<double>& A, long long M, long long j) {
+// upper envelope of A (lower envelope of Hr) on the cell that holds offset |j| (both are smooth on the scale of a cell)
+inline void kb_curve_at(const KbCurve& c, long long M, long long j, double& a, double& hr) {
     if (j < 0) j = -j;
     const double u = (double)j / (double)(M / 2) * (double)KB_NA;
-    if (!(u < (double)KB_NA)) return 1e300;   // at or beyond M / 2: the image is as close as the component itself
+    if (!(u < (double)KB_NA)) { a = 1e300; hr = 0.0; return; }   // at or beyond M / 2: the image is as close as the component itself
     const int i = (int)u;
-    return std::max(A[(size_t)i], A[(size_t)i + 1]);
+    a = std::max(c.A[(size_t)i], c.A[(size_t)i + 1]);
+    hr = std::min(c.Hr[(size_t)i], c.Hr[(size_t)i + 1]);
 }
 
 // magnitude (any positive scale per frequency) of frequency fi's spectrum at data bin k
@@ -756,13 +772,14 @@ inline double spec_mag_host(const HostPlan& hp, int fi, long long k) {
 // and the resample band [rlo, rhi) outside of which the weight is below eps_rs.
 struct RowProfile {
     std::vector<long long> pos;
-    std::vector<double> w;
+    std::vector<double> w;      // upper bound of |W| / max|W| on the cell
+    std::vector<double> w2;     // lower bound of the cell's mean (|W| / max|W|)^2
     long long rlo = 0, rhi = 0;
 };
 inline void row_profile(const HostPlan& hp, int fi, double eps_rs, RowProfile& rp) {
     const FreqRec& r = hp.rec[(size_t)fi];
     const long long lo = r.lo, hi = r.hi, B = hi - lo;
-    rp.pos.clear(); rp.w.clear();
+    rp.pos.clear(); rp.w.clear(); rp.w2.clear();
     rp.rlo = rp.rhi = lo;
     if (B <= 0) return;
     const int NS = (int)std::min<long long>(B, 384);
@@ -771,12 +788,18 @@ inline void row_profile(const HostPlan& hp, int fi, double eps_rs, RowProfile& r
     for (int s = 0; s <= NS; ++s) rp.pos[(size_t)s] = lo + (long long)((double)B * (double)s / (double)NS);
     rp.pos[(size_t)NS] = hi;
     rp.w.assign((size_t)NS, 0.0);
+    rp.w2.assign((size_t)NS, 0.0);
     double peak = 0.0;
     if (hp.family == FAM_TABLE) {   // arbitrary shape: true maximum of every cell
         for (int s = 0; s < NS; ++s) {
-            double m = 0.0;
-            for (long long k = rp.pos[(size_t)s]; k < rp.pos[(size_t)s + 1]; ++k) m = std::max(m, spec_mag_host(hp, fi, k));
+            double m = 0.0, q = 0.0;
+            for (long long k = rp.pos[(size_t)s]; k < rp.pos[(size_t)s + 1]; ++k) {
+                const double v = spec_mag_host(hp, fi, k);
+                m = std::max(m, v);
+                q += v * v;
+            }
             rp.w[(size_t)s] = m;
+            rp.w2[(size_t)s] = q / (double)std::max<long long>(1, rp.pos[(size_t)s + 1] - rp.pos[(size_t)s]);
             peak = std::max(peak, m);
         }
     } else {                        // smooth, single-peaked (Morlet: two-term) spectra: cell ends, the maximum refined by bisection
@@ -791,28 +814,49 @@ inline void row_profile(const HostPlan& hp, int fi, double eps_rs, RowProfile& r
             peak = std::max(peak, std::max(v1, v2));
             if (v1 < v2) a = m1; else c = m2;
         }
-        for (int s = 0; s < NS; ++s) rp.w[(size_t)s] = std::max(mag[(size_t)s], mag[(size_t)s + 1]);
+        for (int s = 0; s < NS; ++s) {
+            rp.w[(size_t)s] = std::max(mag[(size_t)s], mag[(size_t)s + 1]);
+            const double lo2 = std::min(mag[(size_t)s], mag[(size_t)s + 1]);
+            rp.w2[(size_t)s] = lo2 * lo2;
+        }
         for (int s = std::max(0, sm - 1); s < std::min(NS, sm + 1); ++s) rp.w[(size_t)s] = peak;
     }
-    if (!(peak > 0.0)) { rp.pos.clear(); rp.w.clear(); return; }
+    if (!(peak > 0.0)) { rp.pos.clear(); rp.w.clear(); rp.w2.clear(); return; }
     for (double& v : rp.w) v /= peak;
+    for (double& v : rp.w2) v /= peak * peak;
     int s0 = 0, s1 = NS;
     while (s0 < s1 && rp.w[(size_t)s0] < eps_rs) ++s0;
     while (s1 > s0 && rp.w[(size_t)s1 - 1] < eps_rs) --s1;
     rp.rlo = rp.pos[(size_t)s0];
     rp.rhi = rp.pos[(size_t)s1];
 }
-// weighted worst-case error of a row for the alias curve A of a kernel at decimated length M; the row's band is centred
-inline double row_error(const RowProfile& rp, const std::vector<double>& A, long long M) {
+// Error of a row for the alias curve A of a kernel at decimated length M (the row's band is centred): the larger of
+//   * the weighted worst case  max_j w(j) A(j)  - any input, relative to the wavelet's peak gain x the input's spectral mass;
+//   * the relative L2 error for an input with a flat spectrum,  sqrt(sum_j w(j)^2 A(j)^2 / sum_j w(j)^2)  - what a
+//     per-row relative L2 comparison of a broadband signal sees (it exceeds the first when the spectrum has a long
+//     low-level tail, e.g. the |re| + i |im| tables of MexicanHat).
+//   * and the equaliser must not lift any part of the spectrum above RS_MAX_LIFT times its peak: the rounding noise of the
+//     decimated transform is relative to the LARGEST equalised component, and the interpolation passes it at full gain in
+//     the middle of the band (a spectrum with its weight at the band edges, like MexicanHat's tables, would otherwise
+//     get its noise amplified by 1 / Hr(edge)).
+static const double RS_MAX_LIFT = 3.0;
+inline double row_error(const RowProfile& rp, const KbCurve& c, long long M) {
     const long long kc = rp.rlo + (rp.rhi - rp.rlo) / 2;
-    double e = 0.0;
+    double e = 0.0, num = 0.0, den = 0.0;
     for (size_t s = 0; s + 1 < rp.pos.size(); ++s) {
         if (rp.pos[s + 1] <= rp.rlo || rp.pos[s] >= rp.rhi) continue;
         const long long j0 = rp.pos[s] - kc, j1 = rp.pos[s + 1] - 1 - kc;
         const long long j = std::max(j0 < 0 ? -j0 : j0, j1 < 0 ? -j1 : j1);
-        e = std::max(e, rp.w[s] * kb_alias_at(A, M, j));
+        double a, hr;
+        kb_curve_at(c, M, j, a, hr);
+        if (rp.w[s] > RS_MAX_LIFT * hr) return 1e300;
+        const double wa = rp.w[s] * a, cells = (double)(rp.pos[s + 1] - rp.pos[s]);
+        e = std::max(e, wa);
+        num += wa * wa * cells;
+        den += rp.w2[s] * cells;
     }
-    return e;
+    const double l2 = den > 0 ? sqrt(num / den) : 1e300;
+    return std::max(e, l2);
 }
 
 inline void plan_shape_fast(HostPlan& hp);
@@ -929,9 +973,9 @@ inline void plan_multirate(HostPlan& hp) {
     static const int NB = 9;
     auto fb_of = [](int b) { return 0.52 + 0.06 * b; };
     const double PI = 3.14159265358979323846;
-    struct Curve { bool have = false; std::vector<double> A; };
+    struct Curve { bool have = false; KbCurve A; };
     std::vector<Curve> curves(65 * 13 * NB);
-    auto curve = [&](int D, int K, int b) -> const std::vector<double>& {
+    auto curve = [&](int D, int K, int b) -> const KbCurve& {
         Curve& c = curves[((size_t)D * 13 + (size_t)(K / 2)) * NB + (size_t)b];
         if (!c.have) { kb_alias_curve(D, K, fb_of(b) * PI * K, N / D, c.A); c.have = true; }
         return c.A;
@@ -944,7 +988,7 @@ inline void plan_multirate(HostPlan& hp) {
             double best = 1e300;
             int bb = 0;
             for (int b = 0; b < NB; ++b) {
-                const std::vector<double>& A = curve(D, k, b);
+                const KbCurve& A = curve(D, k, b);
                 double e = 0.0;
                 for (int i : rows) {
                     e = std::max(e, row_error(prof[(size_t)i], A, M));

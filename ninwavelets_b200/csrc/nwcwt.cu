@@ -32,16 +32,17 @@ __global__ void __launch_bounds__(512) nwcwt_baseline_rows_kernel(T* rows, long 
     baseline_rows_body<T>(rows, N, mode, lo, hi, sh, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
-// Spectrum bank for inspection: one thread per (frequency, bin).
-template <typename T>
-__global__ void __launch_bounds__(256) nwcwt_bank_kernel(SpecParams<T> sp, cx<T>* bank, int F, long long N) {
+// Spectrum bank for inspection: one thread per (frequency, bin).  TO: the plan's precision (a chirp-z plan keeps its
+// tables in fp64 whatever its I/O precision).
+template <typename T, typename TO = T>
+__global__ void __launch_bounds__(256) nwcwt_bank_kernel(SpecParams<T> sp, cx<TO>* bank, int F, long long N) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
     if (i >= N || f >= F) return;
     const FreqRec r = sp.rec[f];
     cx<T> v = mk<T>((T)0, (T)0);
     if (i >= r.lo && i < r.hi) v = spec_times<T>(sp, r, f, (int)i, mk<T>((T)1, (T)0));
-    bank[(size_t)f * (size_t)N + (size_t)i] = v;
+    bank[(size_t)f * (size_t)N + (size_t)i] = mk<TO>((TO)v.x, (TO)v.y);
 }
 
 // Epoch reductions (mneutils.py:53-55 mean of power, :68-71 inter-trial coherence).
@@ -65,6 +66,107 @@ __global__ void __launch_bounds__(256) nwcwt_reduce_kernel(const void* in, T* ou
         }
         out[i] = nw_hypot(ax / (T)E, ay / (T)E);
     }
+}
+
+// ---- Bluestein (chirp-z) kernels: length-N transforms for ANY N through circular convolutions of a smooth length M >= 2N-1
+// The chirp-z arithmetic runs in fp64 whatever the plan's precision (TI / TO are the plan's I/O types): its rounding error
+// grows with the convolution length, and this is the compatibility path, not the fast one.
+//   X[k] = conj(c[k]) sum_n (x[n] conj(c[n])) c[k - n],   z[n] = (1/N) c[n] sum_k (Y[k] c[k]) conj(c[n - k]),   c[n] = e^{i pi n^2 / N}
+// Every convolution is  T(s; H) = ifft_M(H . fft_M(s))  of a REAL sequence s - exactly what the library's transform with a
+// one-row TABLE plan of length M computes; complex sequences go through as their real and imaginary parts.
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256) nwcwt_blu_pre_fwd_kernel(const TI* x, const cx<T>* chirp, T* in, long long N, long long M) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const size_t s = blockIdx.y;
+    T re = 0, im = 0;
+    if (m < N) {
+        const T v = (T)x[s * (size_t)N + (size_t)m];
+        const cx<T> c = chirp[m];
+        re = v * c.x;
+        im = -v * c.y;
+    }
+    in[(2 * s) * (size_t)M + (size_t)m] = re;
+    in[(2 * s + 1) * (size_t)M + (size_t)m] = im;
+}
+// X[s][k] = conj(c[k]) (Tr[k] + i Ti[k])
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) nwcwt_blu_post_fwd_kernel(const cx<T>* conv, const cx<T>* chirp, cx<TO>* X, long long N, long long M) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const size_t s = blockIdx.y;
+    const cx<T> a = conv[(2 * s) * (size_t)M + (size_t)k], b = conv[(2 * s + 1) * (size_t)M + (size_t)k];
+    const cx<T> u = cmulc(mk<T>(a.x - b.y, a.y + b.x), chirp[k]);
+    X[s * (size_t)N + (size_t)k] = mk<TO>((TO)u.x, (TO)u.y);
+}
+// b[k] = W_f(k) X[k] c[k] on the band, zero elsewhere and on the padding; rows are (signal, frequency) of this chunk
+template <typename T>
+__global__ void __launch_bounds__(256) nwcwt_blu_pre_inv_kernel(SpecParams<T> sp, const cx<T>* X, const cx<T>* chirp, T* in,
+                                                                 long long N, long long M, int F, long long row0) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const size_t r = blockIdx.y;
+    const long long gr = row0 + (long long)r;
+    const long long si = gr / F;
+    const int fi = (int)(gr - si * F);
+    const FreqRec rec = sp.rec[fi];
+    cx<T> b = mk<T>((T)0, (T)0);
+    if (k < N && k >= rec.lo && k < rec.hi) b = cmul(spec_times<T>(sp, rec, fi, (int)k, X[(size_t)si * (size_t)N + (size_t)k]), chirp[k]);
+    in[(2 * r) * (size_t)M + (size_t)k] = b.x;
+    in[(2 * r + 1) * (size_t)M + (size_t)k] = b.y;
+}
+// z[n] = c[n] (Tr[n] + i Ti[n])  ->  cwt / abs / power
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) nwcwt_blu_post_inv_kernel(const cx<T>* conv, const cx<T>* chirp, void* out, long long N,
+                                                                  long long M, long long row0, int mode) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const size_t r = blockIdx.y;
+    const cx<T> a = conv[(2 * r) * (size_t)M + (size_t)n], b = conv[(2 * r + 1) * (size_t)M + (size_t)n];
+    const cx<T> z = cmul(mk<T>(a.x - b.y, a.y + b.x), chirp[n]);
+    const size_t o = (size_t)(row0 + (long long)r) * (size_t)N + (size_t)n;
+    if (mode == OUT_CWT) ((cx<TO>*)out)[o] = mk<TO>((TO)z.x, (TO)z.y);
+    else ((TO*)out)[o] = (TO)real_out<T>(mode, z);
+}
+// table row of the one-row TABLE plan: H = S0 + i S1 (spectra of the filter's real and imaginary parts), or its conjugate
+template <typename T>
+__global__ void __launch_bounds__(256) nwcwt_blu_filter_kernel(const cx<T>* spec, cx<T>* hf, cx<T>* hi, long long M) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const cx<T> a = spec[k], b = spec[(size_t)M + (size_t)k];
+    const cx<T> h = mk<T>(a.x - b.y, a.y + b.x);
+    hf[k] = h;
+    hi[k] = mk<T>(h.x, -h.y);
+}
+
+// Pipe-rate microbenchmark for bench.py's FLOP roofline: 16 independent FFMA2 (fp32) or DFMA (fp64) chains per thread.
+template <typename T>
+__global__ void __launch_bounds__(512) nwcwt_fma_peak_kernel(T* out, int iters, T a, T b) {
+    T v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (T)threadIdx.x * (T)1e-6 + (T)i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] * a + b;   // fp32: the compiler does not pack these; see the float2 variant
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == (T)123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(512) nwcwt_ffma2_peak_kernel(float* out, int iters, float a, float b) {
+    float2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = make_float2(threadIdx.x * 1e-6f + i, threadIdx.x * 2e-6f + i);
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __ffma2_rn(v[i], a2, b2);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i].x + v[i].y;
+    if (s == 123.456f) out[0] = s;
 }
 
 // ---------------------------------------------------------------------------------
@@ -91,6 +193,7 @@ struct nwcwt_plan {
     // device tables
     void *d_tw = nullptr, *d_twA = nullptr, *d_twB = nullptr, *d_twH = nullptr, *d_twL = nullptr;
     void *d_twA2 = nullptr, *d_twB2 = nullptr;   // fast long path
+    int* d_ditpos = nullptr;                     // fast long path: decimation-in-time slot of every pass-A row
     // resampled rows (HostPlan::groups): one sub-plan per group, plus the group's interpolation tables
     struct Group {
         nwcwt_plan* sub = nullptr;
@@ -100,6 +203,11 @@ struct nwcwt_plan {
     };
     std::vector<Group> groups;
     bool is_sub = false;
+    // Bluestein (chirp-z) path for lengths the radix engine cannot factor: hp.path == 4, transforms of length blu_m
+    nwcwt_plan *blu_f = nullptr, *blu_i = nullptr;   // one-row TABLE sub-plans of length blu_m: forward / inverse chirp filter
+    long long blu_m = 0;
+    void *d_chirp = nullptr;        // cx<T>[N]: exp(i pi n^2 / N)
+    int blu_rows = 1;               // rows (pairs of real transforms) per chunk
     // fast long path: launch pairs of consecutive row groups alternate between auxiliary streams so
     // that one group's pass A fills the SMs the previous group's pass-B tail leaves idle
     static const int MAX_AUX = 4;
@@ -124,6 +232,16 @@ struct nwcwt_plan {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Every entry point works on the plan's device and leaves the calling thread's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // ---- launch accounting / optional per-class event timing (bench.py) -----------------------------
 #include <atomic>
@@ -228,12 +346,80 @@ static int upload_tw(void** dptr, long long count, long long P, long long step) 
     return 0;
 }
 
+template <typename T> static int ensure_device_t(nwcwt_plan* pl);
+template <typename T>
+static int run_transform(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
+                         int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
+                         bool forward_only);
+
+// Bluestein plan on the device: the chirp, the frequency records / tables of length N for the spectrum generator, and the
+// chirp filter's spectrum (computed once with the sub-plan's own forward transform), installed as the sub-plan's table.
+template <typename T>
+static int ensure_device_bluestein(nwcwt_plan* pl) {
+    HostPlan& hp = pl->hp;
+    const long long N = hp.N, M = pl->blu_m;
+    int rc;
+    if ((rc = ensure_device_t<T>(pl->blu_f))) return rc;
+    if ((rc = ensure_device_t<T>(pl->blu_i))) return rc;
+    std::vector<cx<T>> c((size_t)N);
+    std::vector<T> h(2 * (size_t)M, (T)0);   // filter c[n], n in (-N, N), wrapped onto M points: real parts, then imaginary parts
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (long long n = 0; n < N; ++n) {
+        const long long q = (long long)(((unsigned long long)n * (unsigned long long)n) % (unsigned long long)(2 * N));
+        const long double a = pi * (long double)q / (long double)N;
+        const long double cr = cosl(a), ci = sinl(a);
+        c[(size_t)n].x = (T)cr;
+        c[(size_t)n].y = (T)ci;
+        h[(size_t)n] = (T)cr;
+        h[(size_t)M + (size_t)n] = (T)ci;
+        if (n > 0) { h[(size_t)(M - n)] = (T)cr; h[(size_t)M + (size_t)(M - n)] = (T)ci; }
+    }
+    CUDA_TRY(cudaMalloc(&pl->d_chirp, sizeof(cx<T>) * (size_t)N));
+    CUDA_TRY(cudaMemcpy(pl->d_chirp, c.data(), sizeof(cx<T>) * (size_t)N, cudaMemcpyHostToDevice));
+    if (hp.F > 0) {
+        CUDA_TRY(cudaMalloc(&pl->d_rec, sizeof(FreqRec) * hp.F));
+        CUDA_TRY(cudaMemcpy(pl->d_rec, hp.rec.data(), sizeof(FreqRec) * hp.F, cudaMemcpyHostToDevice));
+    }
+    if (hp.family == FAM_TABLE) {
+        const size_t cnt = (size_t)hp.F * (size_t)hp.table_len;
+        std::vector<cx<T>> t(cnt);
+        for (size_t i = 0; i < cnt; ++i) { t[i].x = (T)hp.table[2 * i]; t[i].y = (T)hp.table[2 * i + 1]; }
+        CUDA_TRY(cudaMalloc(&pl->d_table, cnt * sizeof(cx<T>)));
+        CUDA_TRY(cudaMemcpy(pl->d_table, t.data(), cnt * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    }
+    // filter spectra: forward transforms of the filter's real and imaginary parts (the sub-plan's own forward kernels),
+    // combined into the table rows of the two one-row TABLE sub-plans
+    T* d_h = nullptr;
+    cx<T>* d_spec = nullptr;
+    void* ws = nullptr;
+    size_t wsb = 0;
+    nwcwt_workspace_bytes(pl->blu_f, 2, &wsb);
+    CUDA_TRY(cudaMalloc((void**)&d_h, sizeof(T) * 2 * (size_t)M));
+    CUDA_TRY(cudaMalloc((void**)&d_spec, sizeof(cx<T>) * 2 * (size_t)M));
+    if (wsb) CUDA_TRY(cudaMalloc(&ws, wsb));
+    CUDA_TRY(cudaMemcpy(d_h, h.data(), sizeof(T) * 2 * (size_t)M, cudaMemcpyHostToDevice));
+    rc = run_transform<T>(pl->blu_f, d_h, nullptr, d_spec, 2, 0, 0, 0, 0, ws, wsb, 0, true);
+    if (!rc) {
+        nwcwt_blu_filter_kernel<T><<<(unsigned)((M + 255) / 256), 256>>>(d_spec, (cx<T>*)pl->blu_f->d_table, (cx<T>*)pl->blu_i->d_table, M);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(NWCWT_ERR_CUDA, std::string("bluestein filter: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_h);
+    cudaFree(d_spec);
+    if (ws) cudaFree(ws);
+    if (rc) return rc;
+    pl->on_device = true;
+    return 0;
+}
+
 template <typename T>
 static int ensure_device_t(nwcwt_plan* pl) {
     HostPlan& hp = pl->hp;
     CUDA_TRY(cudaSetDevice(hp.device));
     if (pl->on_device) return 0;
     int rc;
+    if (hp.path == 4) return ensure_device_bluestein<double>(pl);
     if (hp.path == 0) {
         if ((rc = upload_tw<T>(&pl->d_tw, hp.N, hp.N, 1))) return rc;
     } else {
@@ -247,6 +433,10 @@ static int ensure_device_t(nwcwt_plan* pl) {
         if (hp.fast) {
             if ((rc = upload_tw<T>(&pl->d_twA2, hp.N1f, hp.N1f, 1))) return rc;
             if ((rc = upload_tw<T>(&pl->d_twB2, hp.N2f, hp.N2f, 1))) return rc;
+            std::vector<int> pos((size_t)hp.N1f);
+            for (int k1 = 0; k1 < hp.N1f; ++k1) pos[(size_t)k1] = fft2_dit_pos(hp.stA2, k1);
+            CUDA_TRY(cudaMalloc((void**)&pl->d_ditpos, pos.size() * sizeof(int)));
+            CUDA_TRY(cudaMemcpy(pl->d_ditpos, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
     }
     if (hp.path == 1 && hp.fast && !getenv("NWCWT_NO_WTAB")) {
@@ -290,7 +480,7 @@ static int ensure_device_t(nwcwt_plan* pl) {
                 pl->l2_window_max = (size_t)(v > 0 ? v : 0);
                 if (pl->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, pl->l2_persist_max);
             }
-            int ns = pl->is_sub ? 1 : 2;
+            int ns = pl->is_sub ? 1 : (hp.groups.empty() ? 2 : 3);   // resampled rows: three kernels per launch group (measured 9.0 vs 10.1 ms on cfg2)
             if (const char* e = getenv("NWCWT_STREAMS")) ns = pl->is_sub ? 1 : atoi(e);
             ns = ns < 1 ? 1 : ns > nwcwt_plan::MAX_AUX ? nwcwt_plan::MAX_AUX : ns;
             if (ns > 1) {
@@ -408,6 +598,38 @@ static int launch_short2(nwcwt_plan* pl, const void* signals, void* out, long lo
     return 0;
 }
 
+// fused epoch reductions on the short-row kernel: one CTA per (channel, share of the frequency groups)
+template <typename T>
+static int launch_short2_epochs_t(nwcwt_plan* pl, const void* signals, void* out, long long C, long long E, int kind, void* acc,
+                                  cudaStream_t stream) {
+    const HostPlan& hp = pl->hp;
+    Short2Params<T> P;
+    memset(&P, 0, sizeof(P));
+    P.signals = (const T*)signals;
+    P.out = out;
+    P.N = (int)hp.N;
+    P.F = hp.F;
+    P.S = (int)(C * E);
+    P.tpsh = hp.tpshS;
+    P.st = hp.stS;
+    P.tw = (const cx<T>*)pl->d_tw;
+    P.sp = make_spec<T>(pl);
+    P.n_epochs = (int)E;
+    P.acc = (cx<T>*)acc;
+    const int ngroups = (hp.F + (1 << hp.tpshS) - 1) >> hp.tpshS;
+    const long long target = 6LL * device_sms(hp.device);
+    long long fs = (target + C - 1) / C;
+    if (fs > ngroups) fs = ngroups;
+    if (fs < 1) fs = 1;
+    P.fsplit = (int)fs;
+    const long long grid = C * fs;
+    if (grid > 2147483647LL) return fail(NWCWT_ERR_INVALID, "too many channels for one launch");
+    int sp = g_no_static ? 0 : static_plan_id(hp.stS, hp.tpshS);
+    if (!has_static_short2<T>(sp)) sp = 0;
+    { LaunchScope ls(0, stream); CUDA_TRY(launch_short2_epochs<T>(sp, kind, P, (unsigned)grid, hp.nthrS2, hp.smem_S2, stream)); }
+    return 0;
+}
+
 template <typename T>
 static int launch_short(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
                         int bl, long long blo, long long bhi, cudaStream_t stream, bool forward_only) {
@@ -471,22 +693,32 @@ static LongParams<T> make_long(nwcwt_plan* pl) {
 
 // intermediate ring of the long path: the forward transforms use the generic two-pass kernels,
 // the inverse ones the fast kernels when the plan has them; one region serves both (and the groups' sub-plans)
+// One stream slot of the rings holds the rows of one launch group of ANY of the plan's transforms (the plan's own exact
+// rows or a resampled group's decimated rows): the slot size is the maximum over them, so that launch groups of
+// different decimations running on different streams never overlap.
+static size_t tm_slot_elems(const nwcwt_plan* pl) {
+    size_t e = pl->hp.fast ? (size_t)pl->hp.ring2 * (size_t)pl->hp.tm_stride2 : 0;
+    for (const nwcwt_plan::Group& g : pl->groups) e = std::max(e, tm_slot_elems(g.sub));
+    return e;
+}
+static size_t y_slot_elems(const nwcwt_plan* pl) {
+    size_t e = 0;
+    for (size_t gi = 0; gi < pl->groups.size(); ++gi) {
+        const HostPlan& sh = pl->groups[gi].sub->hp;
+        if (pl->hp.groups[gi].D > 1) e = std::max(e, (size_t)sh.ring2 * (size_t)sh.N);
+    }
+    return e;
+}
 static size_t tm_ring_bytes(const nwcwt_plan* pl) {
     const HostPlan& hp = pl->hp;
     const size_t cs = cx_size(hp.dtype);
     size_t b = hp.generic_ok ? (size_t)hp.ring * hp.tm_stride * cs : 0;
-    if (hp.fast) b = std::max<size_t>(b, (size_t)nwcwt_plan::MAX_AUX * (size_t)hp.ring2 * (size_t)hp.tm_stride2 * cs);
-    for (const nwcwt_plan::Group& g : pl->groups) b = std::max(b, tm_ring_bytes(g.sub));
+    b = std::max<size_t>(b, (size_t)nwcwt_plan::MAX_AUX * tm_slot_elems(pl) * cs);
     return align_up(b, 256);
 }
-// decimated rows of the resampled groups: per stream slot, the rows of one launch pair
+// decimated rows of the resampled groups: per stream slot, the rows of one launch group
 static size_t y_ring_bytes(const nwcwt_plan* pl) {
-    size_t b = 0;
-    for (size_t gi = 0; gi < pl->groups.size(); ++gi) {
-        const HostPlan& sh = pl->groups[gi].sub->hp;
-        if (pl->hp.groups[gi].D > 1) b = std::max(b, (size_t)sh.ring2 * (size_t)sh.N * cx_size(sh.dtype));
-    }
-    return align_up(b * nwcwt_plan::MAX_AUX, 256);
+    return align_up(y_slot_elems(pl) * cx_size(pl->hp.dtype) * nwcwt_plan::MAX_AUX, 256);
 }
 
 template <typename T>
@@ -507,6 +739,7 @@ static Long2Params<T> make_long2(const nwcwt_plan* pl) {
     P.twB = (const cx<T>*)pl->d_twB2;
     P.twH = (const cx<T>*)pl->d_twH;
     P.twL = (const cx<T>*)pl->d_twL;
+    P.ditpos = pl->d_ditpos;
     P.lb = hp.lb;
     P.tm_stride = hp.tm_stride2;
     P.sp = make_spec<T>(pl);
@@ -536,6 +769,7 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
     const unsigned tB = (unsigned)((eh.N1f + (2 << eh.tpshB) - 1) / (2 << eh.tpshB));
     const long long rows = (long long)gs * eh.F;
     const int ns = pl->n_aux;
+    const size_t tm_slot = tm_slot_elems(pl), y_slot = y_slot_elems(pl);   // slot sizes common to all groups of the plan
     // kernels specialised for this plan at compile time, where the library has them
     int spA = g_no_static ? 0 : static_plan_id(eh.stA2, eh.tpshA), spB = g_no_static ? 0 : static_plan_id(eh.stB2, eh.tpshB);
     if (!Long2Dispatch<T>::has(eh.cfgA, 0, spA)) spA = 0;
@@ -577,11 +811,11 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
         const int slot = ns > 1 ? launch_idx % ns : 0;
         cudaStream_t st = ns > 1 ? pl->aux[slot] : stream;
         Q.row0 = (int)r0;
-        Q.Tm = Tm + (size_t)slot * (size_t)eh.ring2 * (size_t)eh.tm_stride2;
+        Q.Tm = Tm + (size_t)slot * tm_slot;
         Q.narrow = group_narrow(eh, r0, g) ? 1 : 0;
         cx<T>* yslot = nullptr;
         if (D > 1) {
-            yslot = Y + (size_t)slot * (size_t)eh.ring2 * (size_t)eh.N;
+            yslot = Y + (size_t)slot * y_slot;
             Q.out = (char*)yslot - (size_t)r0 * (size_t)eh.N * sizeof(cx<T>);   // pass B indexes rows from row0
         }
         { LaunchScope ls(3, st); CUDA_TRY(Long2Dispatch<T>::A(eh.cfgA, spA, Q, dim3(tA, g), eh.nthrA2, eh.smem_A2, st)); }
@@ -694,10 +928,74 @@ static int launch_long(nwcwt_plan* pl, const void* signals, void* out, void* spe
     return 0;
 }
 
+// workspace of a Bluestein plan: spectra of blu_rows signals, the real inputs and complex results of one chunk of
+// convolutions (2 blu_rows sequences of length blu_m each), and the sub-plans' own workspace
+static size_t bluestein_ws_bytes(const nwcwt_plan* pl) {
+    const size_t rs = 8, R2 = 2 * (size_t)pl->blu_rows, M = (size_t)pl->blu_m;   // fp64 internals
+    size_t sub = 0;
+    nwcwt_workspace_bytes(pl->blu_f, (int64_t)R2, &sub);
+    return align_up((size_t)pl->blu_rows * (size_t)pl->hp.N * 2 * rs, 256) + align_up(R2 * M * rs, 256) +
+           align_up(R2 * M * 2 * rs, 256) + align_up(sub, 256);
+}
+
+template <typename TIO>
+static int launch_bluestein(nwcwt_plan* pl, const void* signals, void* out, void* spectra_out, long long S, int output,
+                            int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
+                            bool forward_only) {
+    typedef double T;   // internal precision of the chirp-z path
+    const HostPlan& hp = pl->hp;
+    const long long N = hp.N, M = pl->blu_m;
+    const int RB = pl->blu_rows;
+    if (ws_bytes < bluestein_ws_bytes(pl) || !ws) return fail(NWCWT_ERR_WORKSPACE, "workspace too small");
+    const size_t R2 = 2 * (size_t)RB;
+    char* p = (char*)ws;
+    cx<T>* X = (cx<T>*)p;                 p += align_up((size_t)RB * (size_t)N * sizeof(cx<T>), 256);
+    T* in = (T*)p;                        p += align_up(R2 * (size_t)M * sizeof(T), 256);
+    cx<T>* conv = (cx<T>*)p;              p += align_up(R2 * (size_t)M * sizeof(cx<T>), 256);
+    void* sub_ws = p;
+    size_t sub_bytes = 0;
+    nwcwt_workspace_bytes(pl->blu_f, (int64_t)R2, &sub_bytes);
+    const cx<T>* chirp = (const cx<T>*)pl->d_chirp;
+    const size_t esz = (output == NWCWT_OUT_CWT) ? sizeof(cx<TIO>) : sizeof(TIO);
+    const unsigned gM = (unsigned)((M + 255) / 256), gN = (unsigned)((N + 255) / 256);
+    SpecParams<T> sp = make_spec<T>(pl);
+    int rc;
+    for (long long s0 = 0; s0 < S; s0 += RB) {
+        const int gs = (int)std::min<long long>(RB, S - s0);
+        cx<TIO>* Xout = (cx<TIO>*)spectra_out + (size_t)s0 * (size_t)N;
+        // forward (scipy.fftpack.fft, base.py:399): X = conj(c) . T(x conj(c); Hf)
+        { LaunchScope ls(1, stream); nwcwt_blu_pre_fwd_kernel<TIO, T><<<dim3(gM, gs), 256, 0, stream>>>((const TIO*)signals + (size_t)s0 * (size_t)N, chirp, in, N, M); }
+        if ((rc = run_transform<T>(pl->blu_f, in, conv, nullptr, 2 * gs, NWCWT_OUT_CWT, 0, 0, 0, sub_ws, sub_bytes, stream, false))) return rc;
+        {
+            LaunchScope ls(2, stream);
+            if (forward_only) nwcwt_blu_post_fwd_kernel<T, TIO><<<dim3(gN, gs), 256, 0, stream>>>(conv, chirp, Xout, N, M);
+            else nwcwt_blu_post_fwd_kernel<T, T><<<dim3(gN, gs), 256, 0, stream>>>(conv, chirp, X, N, M);
+        }
+        if (forward_only) continue;
+        // inverse (ifft, base.py:404/406), rows (signal, frequency) in chunks: z = c . T(W X c; conj Hf) / N
+        void* out_s0 = (char*)out + (size_t)s0 * (size_t)hp.F * (size_t)N * esz;
+        const long long rows = (long long)gs * hp.F;
+        for (long long r0 = 0; r0 < rows; r0 += RB) {
+            const int g = (int)std::min<long long>(RB, rows - r0);
+            { LaunchScope ls(3, stream); nwcwt_blu_pre_inv_kernel<T><<<dim3(gM, g), 256, 0, stream>>>(sp, X, chirp, in, N, M, hp.F, r0); }
+            if ((rc = run_transform<T>(pl->blu_i, in, conv, nullptr, 2 * g, NWCWT_OUT_CWT, 0, 0, 0, sub_ws, sub_bytes, stream, false))) return rc;
+            { LaunchScope ls(4, stream); nwcwt_blu_post_inv_kernel<T, TIO><<<dim3(gN, g), 256, 0, stream>>>(conv, chirp, out_s0, N, M, r0, output); }
+        }
+        if (bl != NWCWT_BL_NONE) {
+            LaunchScope ls(5, stream);
+            nwcwt_baseline_rows_kernel<TIO><<<(unsigned)rows, 512, 0, stream>>>((TIO*)out_s0, N, bl, (int)blo, (int)bhi);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename T>
 static int run_transform(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
                          int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
                          bool forward_only) {
+    if (pl->hp.path == 4)
+        return launch_bluestein<T>(pl, signals, out, spectra, S, output, bl, blo, bhi, ws, ws_bytes, stream, forward_only);
     if (pl->hp.path == 0)
         return launch_short<T>(pl, signals, out, spectra, S, output, bl, blo, bhi, stream, forward_only);
     return launch_long<T>(pl, signals, out, spectra, S, output, bl, blo, bhi, ws, ws_bytes, stream, forward_only);
@@ -723,8 +1021,38 @@ static int check_args(const nwcwt_plan* pl, int output, int bl, long long& blo, 
 // ---------------------------------------------------------------------------------
 extern "C" {
 
+int nwcwt_plan_create(nwcwt_plan** out, const nwcwt_plan_desc* d);
+
 int nwcwt_version(void) { return NWCWT_VERSION; }
 int64_t nwcwt_launch_count(void) { return g_launches.load(); }
+
+int nwcwt_fma_peak(int32_t device, int32_t dtype, double* lane_ops_per_s) {
+    if (!lane_ops_per_s) return fail(NWCWT_ERR_INVALID, "null argument");
+    DeviceGuard guard(device);
+    void* buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int sms = device_sms(device), grid = sms * 4, nthr = 512, iters = 4096;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, 0);
+        if (dtype == NWCWT_F32) nwcwt_ffma2_peak_kernel<<<grid, nthr>>>((float*)buf, iters, 0.999f, 1e-3f);
+        else nwcwt_fma_peak_kernel<double><<<grid, nthr>>>((double*)buf, iters, 0.999, 1e-3);
+        cudaEventRecord(e1, 0);
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    const double lanes = (dtype == NWCWT_F32 ? 2.0 : 1.0) * 16.0 * (double)iters * (double)nthr * (double)grid;
+    *lane_ops_per_s = lanes / ((double)best * 1e-3);
+    return 0;
+}
 
 int nwcwt_debug_force_generic(int32_t on) {
     g_force_generic = on != 0;
@@ -763,6 +1091,39 @@ int nwcwt_profile_read(double ms[8], int64_t launches[8]) {
     return 0;
 }
 const char* nwcwt_last_error(void) { return g_err.c_str(); }
+
+// Bluestein plan: smallest 2-3-5-smooth M >= 2 n - 1 that the engine plans, two one-row TABLE sub-plans of that length
+static int plan_bluestein(nwcwt_plan* pl, std::string& err) {
+    HostPlan& hp = pl->hp;
+    const long long need = 2 * hp.N - 1;
+    if (need >= (1LL << 30)) { err = "signal length too large for the chirp-z path"; return NWCWT_ERR_UNSUPPORTED; }
+    long long M = 0;
+    for (long long p5 = 1; p5 <= 4 * need; p5 *= 5)
+        for (long long p3 = p5; p3 <= 4 * need; p3 *= 3) {
+            long long v = p3;
+            while (v < need) v *= 2;
+            if (M == 0 || v < M) M = v;
+        }
+    std::vector<double> zero_table(2 * (size_t)M, 0.0);
+    double f1 = 1.0;
+    for (int which = 0; which < 2; ++which) {
+        nwcwt_plan_desc d;
+        memset(&d, 0, sizeof(d));
+        d.device = hp.device; d.dtype = NWCWT_F64; d.family = NWCWT_TABLE; d.interpolate = 0;
+        d.n = M; d.n_freqs = 1; d.resample = -1; d.sfreq = hp.sfreq; d.freqs = &f1;
+        d.table = zero_table.data(); d.table_len = M; d.prune_eps = 0.0;
+        nwcwt_plan* sub = nullptr;
+        int rc = nwcwt_plan_create(&sub, &d);
+        if (rc) { err = std::string("chirp-z sub-plan: ") + nwcwt_last_error(); return rc; }
+        sub->is_sub = true;
+        (which ? pl->blu_i : pl->blu_f) = sub;
+    }
+    hp.path = 4;
+    pl->blu_m = M;
+    const size_t per_row = (size_t)M * 48;
+    pl->blu_rows = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)256 << 20) / per_row));
+    return 0;
+}
 
 int nwcwt_plan_create(nwcwt_plan** out, const nwcwt_plan_desc* d) {
     if (!out || !d) return fail(NWCWT_ERR_INVALID, "null argument");
@@ -805,8 +1166,12 @@ int nwcwt_plan_create(nwcwt_plan** out, const nwcwt_plan_desc* d) {
     plan_bands(hp);
     std::string err;
     if (!plan_shape(hp, err)) {
-        delete pl;
-        return fail(NWCWT_ERR_UNSUPPORTED, err);
+        // no radix plan for this length (a prime factor > 64): Bluestein's algorithm on a smooth length >= 2n - 1
+        int rc = plan_bluestein(pl, err);
+        if (rc) {
+            delete pl;
+            return fail(rc, err);
+        }
     }
     for (const MrGroup& mg : hp.groups) {
         nwcwt_plan::Group g;
@@ -830,9 +1195,12 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
         nwcwt_plan_destroy(g.sub);
     }
     pl->groups.clear();
+    if (pl->blu_f) nwcwt_plan_destroy(pl->blu_f);
+    if (pl->blu_i) nwcwt_plan_destroy(pl->blu_i);
+    pl->blu_f = pl->blu_i = nullptr;
     if (pl->on_device || pl->h_stream[0]) {
         cudaSetDevice(pl->hp.device);
-        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_wtab, pl->d_twA2, pl->d_twB2,
+        void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_wtab, pl->d_ditpos, pl->d_chirp, pl->d_twA2, pl->d_twB2,
                         pl->h_in_dev[0], pl->h_in_dev[1], pl->h_out_dev[0], pl->h_out_dev[1], pl->h_ws[0], pl->h_ws[1]};
         for (void* p : ptrs)
             if (p) cudaFree(p);
@@ -865,6 +1233,11 @@ int nwcwt_plan_get_info(const nwcwt_plan* pl, nwcwt_plan_info* info) {
         info->group_n1[g] = mg.sub->N1f;
         info->group_n2[g] = mg.sub->N2f;
         info->group_err[g] = mg.err;
+    }
+    if (hp.path == 4) {
+        info->n1 = (int32_t)pl->blu_m;   // chirp-z: transforms of this length
+        info->rows_per_launch = pl->blu_rows;
+        return 0;
     }
     if (hp.path == 0) {
         info->batch = 1 << hp.tsh;
@@ -921,6 +1294,10 @@ int nwcwt_workspace_bytes(const nwcwt_plan* pl, int64_t n_signals, size_t* bytes
     if (!pl || !bytes) return fail(NWCWT_ERR_INVALID, "null argument");
     (void)n_signals;
     const HostPlan& hp = pl->hp;
+    if (hp.path == 4) {
+        *bytes = bluestein_ws_bytes(pl);
+        return 0;
+    }
     if (hp.path == 0) {
         *bytes = 0;
         return 0;
@@ -932,12 +1309,17 @@ int nwcwt_workspace_bytes(const nwcwt_plan* pl, int64_t n_signals, size_t* bytes
 
 int nwcwt_spectrum_bank(nwcwt_plan* pl, void* bank, void* stream) {
     if (!pl || !bank) return fail(NWCWT_ERR_INVALID, "null argument");
+    DeviceGuard guard(pl->hp.device);
     int rc = ensure_device(pl);
     if (rc) return rc;
     const HostPlan& hp = pl->hp;
     if (hp.F <= 0) return 0;
     dim3 grid((unsigned)((hp.N + 255) / 256), (unsigned)hp.F);
-    if (hp.dtype == NWCWT_F32) {
+    if (hp.path == 4 && hp.dtype == NWCWT_F32) {   // chirp-z plan: fp64 tables
+        SpecParams<double> sp = make_spec<double>(pl);
+        sp.norm = 1.0;
+        nwcwt_bank_kernel<double, float><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, (cx<float>*)bank, hp.F, hp.N);
+    } else if (hp.dtype == NWCWT_F32) {
         SpecParams<float> sp = make_spec<float>(pl);
         sp.norm = 1.0f;
         nwcwt_bank_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, (cx<float>*)bank, hp.F, hp.N);
@@ -954,7 +1336,7 @@ int nwcwt_reduce_epochs(nwcwt_plan* pl, const void* in, void* out, int64_t E, in
                         void* stream) {
     if (!pl || !in || !out) return fail(NWCWT_ERR_INVALID, "null argument");
     if (E <= 0 || count <= 0 || kind < 0 || kind > 1) return fail(NWCWT_ERR_INVALID, "bad reduction arguments");
-    CUDA_TRY(cudaSetDevice(pl->hp.device));
+    DeviceGuard guard(pl->hp.device);
     const unsigned grid = (unsigned)((count + 255) / 256);
     LaunchScope ls(5, (cudaStream_t)stream);
     if (pl->hp.dtype == NWCWT_F32)
@@ -963,6 +1345,24 @@ int nwcwt_reduce_epochs(nwcwt_plan* pl, const void* in, void* out, int64_t E, in
         nwcwt_reduce_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(in, (double*)out, E, count, kind);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+int nwcwt_transform_epochs(nwcwt_plan* pl, const void* signals, void* out, int64_t n_channels, int64_t n_epochs,
+                           int32_t kind, void* ws, size_t ws_bytes, void* stream) {
+    if (!pl || !signals || !out) return fail(NWCWT_ERR_INVALID, "null argument");
+    if (n_channels <= 0 || n_epochs <= 0 || kind < 0 || kind > 1) return fail(NWCWT_ERR_INVALID, "bad epoch arguments");
+    if (pl->hp.F <= 0) return fail(NWCWT_ERR_INVALID, "plan has no frequencies");
+    if (pl->hp.path != 0 || !pl->hp.short2)
+        return fail(NWCWT_ERR_UNSUPPORTED, "fused epoch reductions need rows that fit one CTA (short packed path); "
+                                           "use nwcwt_transform + nwcwt_reduce_epochs for this length");
+    const size_t need = kind == 1 ? (size_t)n_channels * (size_t)pl->hp.F * (size_t)pl->hp.N * cx_size(pl->hp.dtype) : 0;
+    if (ws_bytes < need || (need && !ws)) return fail(NWCWT_ERR_WORKSPACE, "workspace too small");
+    DeviceGuard guard(pl->hp.device);
+    int rc = ensure_device(pl);
+    if (rc) return rc;
+    if (pl->hp.dtype == NWCWT_F32)
+        return launch_short2_epochs_t<float>(pl, signals, out, n_channels, n_epochs, kind, ws, (cudaStream_t)stream);
+    return launch_short2_epochs_t<double>(pl, signals, out, n_channels, n_epochs, kind, ws, (cudaStream_t)stream);
 }
 
 int nwcwt_baseline_rows(int32_t device, int32_t dtype, void* rows, int64_t n_rows, int64_t n, int32_t bl,
@@ -974,7 +1374,7 @@ int nwcwt_baseline_rows(int32_t device, int32_t dtype, void* rows, int64_t n_row
     if (blo < 0 || bhi < 0) return fail(NWCWT_ERR_INVALID, "negative baseline index");
     if (bhi > n) bhi = n;
     if (blo > bhi) blo = bhi;
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
     LaunchScope ls(5, (cudaStream_t)stream);
     if (dtype == NWCWT_F32)
         nwcwt_baseline_rows_kernel<float><<<(unsigned)n_rows, 512, 0, (cudaStream_t)stream>>>((float*)rows, n, bl, (int)blo, (int)bhi);
@@ -988,6 +1388,7 @@ int nwcwt_forward(nwcwt_plan* pl, const void* signals, void* spectra, int64_t S,
                   void* stream) {
     if (!pl || !signals || !spectra) return fail(NWCWT_ERR_INVALID, "null argument");
     if (S <= 0) return 0;
+    DeviceGuard guard(pl->hp.device);
     int rc = ensure_device(pl);
     if (rc) return rc;
     if (pl->hp.dtype == NWCWT_F32)
@@ -1002,6 +1403,7 @@ int nwcwt_transform(nwcwt_plan* pl, const void* signals, void* out, int64_t S, i
     if (rc) return rc;
     if (!signals || !out) return fail(NWCWT_ERR_INVALID, "null buffer");
     if (S <= 0) return 0;
+    DeviceGuard guard(pl->hp.device);
     if ((rc = ensure_device(pl))) return rc;
     if (pl->hp.dtype == NWCWT_F32)
         return run_transform<float>(pl, signals, out, nullptr, S, output, bl, lo, hi, ws, ws_bytes, (cudaStream_t)stream, false);
@@ -1015,6 +1417,7 @@ int nwcwt_transform_host(nwcwt_plan* pl, const void* signals, void* out, int64_t
     if (rc) return rc;
     if (!signals || !out) return fail(NWCWT_ERR_INVALID, "null buffer");
     if (S <= 0) return 0;
+    DeviceGuard guard(pl->hp.device);
     if ((rc = ensure_device(pl))) return rc;
     const HostPlan& hp = pl->hp;
     const size_t rs = hp.dtype == NWCWT_F32 ? 4 : 8;

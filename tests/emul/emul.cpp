@@ -143,6 +143,9 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup
     Q.stA = eh.stA2; Q.stB = eh.stB2; Q.twA = twA2.data(); Q.twB = twB2.data(); Q.twH = twH.data(); Q.twL = twL.data();
     Q.lb = eh.lb; Q.tm_stride = eh.tm_stride2; Q.sp = make_sp<T>(eh, table);
     if (have_wtab) Q.sp.wtab = wtab.data();
+    std::vector<int> ditpos((size_t)eh.N1f);
+    for (int k1 = 0; k1 < eh.N1f; ++k1) ditpos[(size_t)k1] = fft2_dit_pos(eh.stA2, k1);
+    if (!(g_mode & 256)) Q.ditpos = ditpos.data();
     const int ring2 = eh.ring2 < 3 ? eh.ring2 : 3;
     std::vector<cx<T>> Tm2((size_t)ring2 * eh.tm_stride2), Y;
     Q.X = X; Q.Tm = Tm2.data();

@@ -45,9 +45,19 @@ def test_short_and_long_shapes():
         assert plan(1 << e, [1.0, 2.0]).info()["n1"] * plan(1 << e, [1.0, 2.0]).info()["n2"] == 1 << e
 
 
-def test_unsupported_lengths_and_bad_args():
+def test_any_length_plans_and_bad_args():
+    # a prime factor > 64: no radix plan, the chirp-z (Bluestein) path on a smooth length >= 2 n - 1 (host planning only here)
+    for n in (2 * 10007, 100003, 1234, 599999, 600001):
+        i = plan(n, [1.0, 2.0]).info()
+        assert i["path"] == "chirp_z" and i["n1"] >= 2 * n - 1 and i["n1"] < 4 * n, (n, i)
+        m = i["n1"]
+        for p in (2, 3, 5):
+            while m % p == 0:
+                m //= p
+        assert m == 1
+        assert plan(n, [1.0, 2.0]).workspace_bytes(4) > 0
     with pytest.raises(be.BackendError) as ei:
-        plan(2 * 10007, [1.0, 2.0])            # prime factor > 64
+        plan((1 << 31) + 1, [1.0, 2.0])
     assert ei.value.code == be.ERR_UNSUPPORTED
     with pytest.raises(ZeroDivisionError):      # reference base.py:234-235
         plan(300, [1.0, 0.0])

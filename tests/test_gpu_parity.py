@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import cwt_oracle as orc
-from golden_util import case_wave, l2_rel_err, peak_rel_err
+from golden_util import case_floor, case_wave, l2_rel_err, peak_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -46,16 +46,17 @@ def test_all_small_golden_cases_fp64(nw, golden_transforms):
         obj = make(nw, c["kind"], c["kw"])
         z = obj.cwt(x, c["freqs"])
         assert z.shape == c["cwt"].shape and z.dtype == np.complex128, name
-        e = peak_rel_err(z, c["cwt"]).max()
+        fl = case_floor(name)                  # zero except for the pure-sine README cases (golden_util.py)
+        e = peak_rel_err(z, c["cwt"], fl).max()
         worst = max(worst, e)
         assert e <= F64_TOL, (name, e)
         p = obj.power(x)                       # cached plan, freqs=None like the reference allows
-        assert peak_rel_err(p, np.abs(c["cwt"]) ** 2).max() <= F64_TOL, name
+        assert peak_rel_err(p, np.abs(c["cwt"]) ** 2, fl).max() <= F64_TOL, name
         a = obj.abs(x)
-        assert peak_rel_err(a, np.abs(c["cwt"])).max() <= F64_TOL, name
+        assert peak_rel_err(a, np.abs(c["cwt"]), fl).max() <= F64_TOL, name
         n += 1
     assert n >= 50
-    print("worst fp64 error over %d golden cases: %.3e" % (n, worst))
+    print("worst fp64 error over %d golden cases (rows relative to themselves; floor only for readme_*): %.3e" % (n, worst))
 
 
 def test_all_small_golden_cases_fp32(nw, golden_transforms):
@@ -67,10 +68,10 @@ def test_all_small_golden_cases_fp32(nw, golden_transforms):
         ref = orc.cwt(orc.Family(c["kind"], **c["kw"]), x32.astype(np.float64), c["freqs"])
         z = make(nw, c["kind"], c["kw"], dtype="float32").cwt(x32, c["freqs"])
         assert z.dtype == np.complex64
-        e = l2_rel_err(z.astype(np.complex128), ref).max()
+        e = l2_rel_err(z.astype(np.complex128), ref, case_floor(name, f32=True)).max()
         worst = max(worst, e)
         assert e <= F32_TOL, (name, e)
-    print("worst fp32 error: %.3e" % worst)
+    print("worst fp32 error (rows relative to themselves; floor only for readme_*): %.3e" % worst)
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
@@ -143,7 +144,8 @@ def test_baseline_modes_and_epochs(nw):
     assert peak_rel_err(zs, e["zscore_power"]).max() <= 1e-10
     zs32 = nw.Morlet(1000, 7., cuda=True, dtype="float32").power(e["data"][:, 1, :].astype(np.float32), e["freqs"],
                                                                  baseline=("zscore", 0.0, 0.2))
-    assert l2_rel_err(zs32, e["zscore_power"]).max() <= 1e-4   # z-score amplifies by mean/std of the window
+    ez = l2_rel_err(zs32, e["zscore_power"]).max()
+    assert ez <= F32_TOL, ez
 
 
 def test_api_quirks_and_extensions(nw):
@@ -200,7 +202,7 @@ def test_user_subclass_plugin(nw):
     assert peak_rel_err(Bump().cwt(x, fr), ref).max() <= F64_TOL
 
 
-@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-5)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 1e-5)])
 def test_properties_at_full_size(nw, dtype, tol):
     """Size-independent checks at a BASELINE.json config-2 row size (N = 600 000)."""
     n = 600000
@@ -209,12 +211,14 @@ def test_properties_at_full_size(nw, dtype, tol):
     m = make(nw, "morse", dict(sfreq=1000), dtype=dtype)
     # (1) unit sinusoid at the analysis frequency has Morse power 1 (peak of the spectrum is exactly 2)
     p = m.power(np.sin(2 * np.pi * 40.0 * t), fr)
-    assert abs(np.median(p[1]) - 1.0) <= 50 * tol and p[0].max() < 1e-6
+    assert abs(np.median(p[1]) - 1.0) <= 10 * tol and p[0].max() < 1e-6, abs(np.median(p[1]) - 1.0)
     # (2) linearity in the signal
     rng = np.random.default_rng(4)
     a, b = rng.standard_normal(n), rng.standard_normal(n)
     za, zb, zab = m.cwt(a, None), m.cwt(b, None), m.cwt(a + 2 * b, None)
-    assert l2_rel_err(zab.astype(np.complex128), (za + 2 * zb).astype(np.complex128)).max() <= 20 * tol
+    # three transforms, each within tol of the exact one: their combination is within 4 tol (|a| + 2 |b| + |a + 2b|)
+    elin = l2_rel_err(zab.astype(np.complex128), (za + 2 * zb).astype(np.complex128)).max()
+    assert elin <= 4 * tol, elin
     # (3) Parseval: sum_n |z|^2 = (1/N) sum_k |W X|^2
     X = np.fft.fft(a)
     k = np.arange(n) * (1 / (n / 1000.0))
@@ -222,7 +226,7 @@ def test_properties_at_full_size(nw, dtype, tol):
         W = orc.analytic_spectrum(orc.Family("morse"), k, f)
         lhs = (np.abs(za[i].astype(np.complex128)) ** 2).sum()
         rhs = (np.abs(W * X) ** 2).sum() / n
-        assert abs(lhs - rhs) / rhs <= 100 * tol
+        assert abs(lhs - rhs) / rhs <= 2 * tol, abs(lhs - rhs) / rhs   # energy: twice the amplitude error
 
 
 def test_forward_fft_entry_point(nw):
@@ -309,14 +313,14 @@ def test_2_26_properties(nw):
     d = (zab - (za + 2 * zb))
     num = torch.sqrt((d.real.double() ** 2 + d.imag.double() ** 2).sum(dim=1))
     den = torch.sqrt((zab.real.double() ** 2 + zab.imag.double() ** 2).sum(dim=1))
-    assert float((num / den).max()) <= 20 * F32_TOL
+    assert float((num / den).max()) <= 4 * F32_TOL, float((num / den).max())
     X = torch.fft.fft(ta[0].double())
     k = np.arange(n) * (1 / (n / 1000.0))
     for i, f in enumerate(fr):
         W = torch.as_tensor(orc.analytic_spectrum(orc.Family("morse"), k, f), device="cuda")
         lhs = float((za[i].real.double() ** 2 + za[i].imag.double() ** 2).sum())
         rhs = float(((W * X).abs() ** 2).sum()) / n
-        assert abs(lhs - rhs) / rhs <= 100 * F32_TOL
+        assert abs(lhs - rhs) / rhs <= 2 * F32_TOL, abs(lhs - rhs) / rhs
 
 
 @pytest.mark.parametrize("n", [50625, 56250, 57344, 98304, 30375, 20000, 16384 + 8192])
@@ -333,9 +337,170 @@ def test_awkward_long_lengths(nw, n):
     x32 = x.astype(np.float32)
     refp = np.stack([orc.baseline_rows(orc.power(fam, xi.astype(np.float64), fr), 1000., 0.1, 0.9, "zscore") for xi in x32])
     p = make(nw, "morlet", dict(sfreq=1000, sigma=7.), dtype="float32").power(x32, fr, baseline=("zscore", 0.1, 0.9))
-    assert l2_rel_err(p.reshape(-1, n).astype(np.float64), refp.reshape(-1, n)).max() <= 3 * F32_TOL, n
+    ep = l2_rel_err(p.reshape(-1, n).astype(np.float64), refp.reshape(-1, n)).max()
+    assert ep <= F32_TOL, (n, ep)
 
 
-def test_unsupported_length_raises(nw):
-    with pytest.raises(Exception):
-        make(nw, "morse", dict(sfreq=1000), dtype="float32").power(np.zeros(100003, dtype=np.float32), [1.0, 2.0])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_resampled_rows_at_cfg2_length(nw, dtype):
+    """Resampled rows at BASELINE.json config-2 row size: power and abs of every row against the oracle,
+    each row relative to itself, and against the same family with resampling switched off."""
+    n = 600000
+    rng = np.random.default_rng(31)
+    t = np.arange(n) / 1000.0
+    x = rng.standard_normal((2, n)) + np.sin(2 * np.pi * 10 * t) + 0.5 * np.sin(2 * np.pi * 60 * t + 1.0)
+    fr = np.array([1.0, 3.0, 7.0, 18.0, 30.0, 55.0, 100.0])
+    fam = orc.Family("morse", sfreq=1000)
+    xin = x.astype(np.float32) if dtype == "float32" else x
+    m = make(nw, "morse", dict(sfreq=1000), dtype=dtype)
+    p = m.power(xin, fr)
+    groups = m._plan.info()["groups"]
+    assert groups and all(g["D"] >= 2 for g in groups), groups          # every row of this plan is resampled
+    ref = np.stack([orc.power(fam, xi.astype(np.float64), fr) for xi in xin])
+    if dtype == "float32":
+        e = l2_rel_err(p.reshape(-1, n).astype(np.float64), ref.reshape(-1, n))
+        assert e.max() <= F32_TOL, e
+        a = m.abs(xin, None)
+        assert l2_rel_err(a.reshape(-1, n).astype(np.float64), np.sqrt(ref).reshape(-1, n)).max() <= F32_TOL
+    else:
+        e = peak_rel_err(p.reshape(-1, n), ref.reshape(-1, n))
+        assert e.max() <= F64_TOL, e
+    exact = make(nw, "morse", dict(sfreq=1000), dtype=dtype, resample=False).power(xin, fr)
+    d = l2_rel_err(p.reshape(-1, n).astype(np.float64), exact.reshape(-1, n).astype(np.float64)).max()
+    assert d <= (F32_TOL if dtype == "float32" else 1e-12), d
+    print("resampled %s: worst row error %.3e, vs exact rows %.3e, groups %s" % (dtype, e.max(), d, [(g["D"], g["K"]) for g in groups]))
+
+
+def test_2_26_against_oracle(nw):
+    """N = 2^26 (config 5's largest row) against the oracle on two frequencies, fp32, rows relative to themselves."""
+    n = 1 << 26
+    rng = np.random.default_rng(8)
+    x32 = rng.standard_normal(n).astype(np.float32)
+    fr = np.array([5.0, 120.0])
+    p = make(nw, "morse", dict(sfreq=1000), dtype="float32").power(x32, fr)
+    ref = orc.power(orc.Family("morse", sfreq=1000), x32.astype(np.float64), fr)
+    e = l2_rel_err(p.astype(np.float64), ref)
+    assert e.max() <= F32_TOL, e
+
+
+def test_interpolate_true_on_long_rows(nw):
+    """`interpolate=True` (the WaveletBase default, base.py:239-242, 276) at N = 600 000: half-grid spectrum, aliased half
+    zeroed; fp64 complex transform and fp32 power against the oracle."""
+    n = 600000
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(n)
+    fr = np.array([2.0, 40.0, 230.0])
+    fam = orc.Family("morse", sfreq=1000, interpolate=True)
+    z = make(nw, "morse", dict(sfreq=1000, interpolate=True), dtype="float64").cwt(x, fr)
+    assert peak_rel_err(z, orc.cwt(fam, x, fr)).max() <= F64_TOL
+    x32 = x.astype(np.float32)
+    p = make(nw, "morse", dict(sfreq=1000, interpolate=True), dtype="float32").power(x32, fr)
+    assert l2_rel_err(p.astype(np.float64), orc.power(fam, x32.astype(np.float64), fr)).max() <= F32_TOL
+
+
+@pytest.mark.parametrize("mode", ["mean", "ratio", "percent", "log", "zlog"])
+def test_fused_baseline_epilogues(nw, mode):
+    """The five Baseline modes other than zscore (base.py:52-68) as epilogues of the fused short-row kernel
+    (`power(..., baseline=)`, N = 1500) and of the long-row path (N = 60 000)."""
+    fam = orc.Family("morlet", sfreq=1000, sigma=7.)
+    fr = np.arange(2, 42.0, 3.0)
+    for n in (1500, 60000):
+        x = orc.meg_epochs_like(4, n) if n == 1500 else np.random.default_rng(3).standard_normal((2, n))
+        ref = np.stack([orc.baseline_rows(orc.power(fam, xi, fr), 1000., 0.1, 0.3, mode) for xi in x])
+        got = make(nw, "morlet", dict(sfreq=1000, sigma=7.), dtype="float64").power(x, fr, baseline=(mode, 0.1, 0.3))
+        assert peak_rel_err(got.reshape(-1, n), ref.reshape(-1, n)).max() <= 1e-11, (mode, n)
+        x32 = x.astype(np.float32)
+        ref32 = np.stack([orc.baseline_rows(orc.power(fam, xi.astype(np.float64), fr), 1000., 0.1, 0.3, mode) for xi in x32])
+        got32 = make(nw, "morlet", dict(sfreq=1000, sigma=7.), dtype="float32").power(x32, fr, baseline=(mode, 0.1, 0.3))
+        e = l2_rel_err(got32.reshape(-1, n).astype(np.float64), ref32.reshape(-1, n)).max()
+        assert e <= F32_TOL, (mode, n, e)
+
+
+@pytest.mark.parametrize("n", [65536, 600000])
+def test_generic_kernels_forced(nw, n):
+    """nwcwt_debug_force_generic: the generic (any factor <= 64) two-pass kernels on lengths the packed kernels normally
+    take, against the oracle and against the packed kernels' own result."""
+    from ninwavelets_b200 import _backend as be
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal(n)
+    fr = np.array([4.0, 33.0, 150.0])
+    fam = orc.Family("morse", sfreq=1000)
+    ref = orc.cwt(fam, x, fr)
+    fast = make(nw, "morse", dict(sfreq=1000), dtype="float64").cwt(x, fr)
+    be.force_generic(True)
+    try:
+        slow = make(nw, "morse", dict(sfreq=1000), dtype="float64").cwt(x, fr)
+        p32 = make(nw, "morse", dict(sfreq=1000), dtype="float32").power(x.astype(np.float32), fr)
+    finally:
+        be.force_generic(False)
+    assert peak_rel_err(slow, ref).max() <= F64_TOL and peak_rel_err(fast, ref).max() <= F64_TOL
+    assert peak_rel_err(slow, fast).max() <= F64_TOL
+    ref32 = orc.power(fam, x.astype(np.float32).astype(np.float64), fr)
+    assert l2_rel_err(p32.astype(np.float64), ref32).max() <= F32_TOL
+
+
+@pytest.mark.parametrize("n_ep", [200, 5])
+def test_fused_epoch_reductions(nw, n_ep):
+    """mneutils.py:53-55 / :68-71 with the reduction over epochs inside the transform kernel (nwcwt_transform_epochs): the
+    (E, F, T) rows are never written.  200 epochs (config 3's count) and an odd count, two channels, against the oracle's
+    per-epoch transforms reduced in fp64."""
+    import torch
+    from ninwavelets_b200 import _backend as be
+    fam = orc.Family("morlet", sfreq=1000, sigma=7.)
+    fr = np.arange(1, 41.0)
+    x = np.stack([orc.meg_epochs_like(n_ep, 1500, seed=3), orc.meg_epochs_like(n_ep, 1500, seed=4)])     # (C, E, T)
+    zref = np.stack([np.stack([orc.cwt(fam, xe, fr) for xe in xc]) for xc in x])                          # (C, E, F, T)
+    pref = (np.abs(zref) ** 2).mean(axis=1)
+    iref = np.abs((zref / np.abs(zref)).mean(axis=1))
+    m = nw.Morlet(1000, 7., cuda=True)
+    m.make_fft_wavelets(fr, 1.5)
+    xt = torch.as_tensor(x, device="cuda")
+    l0 = be.launch_count()
+    p = m._plan.transform_epochs_device(xt, 0).cpu().numpy()
+    assert be.launch_count() - l0 == 1                       # one kernel: nothing is materialised and re-read
+    assert peak_rel_err(p.reshape(-1, 1500), pref.reshape(-1, 1500)).max() <= F64_TOL
+    itc = m._plan.transform_epochs_device(xt, 1).cpu().numpy()
+    assert np.abs(itc - iref).max() <= 1e-12
+    m32 = nw.Morlet(1000, 7., cuda=True, dtype="float32")
+    m32.make_fft_wavelets(fr, 1.5)
+    x32 = x.astype(np.float32)
+    z32 = np.stack([np.stack([orc.cwt(fam, xe.astype(np.float64), fr) for xe in xc]) for xc in x32])
+    p32 = m32._plan.transform_epochs_device(torch.as_tensor(x32, device="cuda"), 0).cpu().numpy()
+    e = l2_rel_err(p32.reshape(-1, 1500).astype(np.float64), (np.abs(z32) ** 2).mean(axis=1).reshape(-1, 1500)).max()
+    assert e <= F32_TOL, e
+    i32 = m32._plan.transform_epochs_device(torch.as_tensor(x32, device="cuda"), 1).cpu().numpy()
+    # the unit phasor z / |z| of a sample whose |z| is far below the row's norm carries that sample's RELATIVE rounding error
+    # (inherent to the definition): the fp32 bar is the per-row relative L2 error, like every other fp32 comparison
+    iref32 = np.abs((z32 / np.abs(z32)).mean(axis=1))
+    ei = l2_rel_err(i32.reshape(-1, 1500).astype(np.float64), iref32.reshape(-1, 1500)).max()
+    assert ei <= F32_TOL, ei
+
+
+@pytest.mark.parametrize("n", [100003, 2 * 10007, 1234, 599999])
+def test_any_length_chirp_z(nw, n):
+    """Lengths with a prime factor > 64 (the reference's scipy.fftpack takes any N, base.py:399, 406): Bluestein's
+    chirp-z algorithm on the packed engine, exact circular semantics; 100 003 is prime."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n))
+    fr = np.array([2.0, 17.0, 140.0])
+    fam = orc.Family("morse", sfreq=1000)
+    m = make(nw, "morse", dict(sfreq=1000), dtype="float64")
+    z = m.cwt(x, fr)
+    assert m._plan.info()["path"] == "chirp_z"
+    ref = np.stack([orc.cwt(fam, xi, fr) for xi in x])
+    assert peak_rel_err(z.reshape(-1, n), ref.reshape(-1, n)).max() <= F64_TOL, n
+    x32 = x.astype(np.float32)
+    refp = np.stack([orc.baseline_rows(orc.power(fam, xi.astype(np.float64), fr), 1000., 0.1, 0.9, "zscore") for xi in x32])
+    p = make(nw, "morse", dict(sfreq=1000), dtype="float32").power(x32, fr, baseline=("zscore", 0.1, 0.9))
+    e = l2_rel_err(p.reshape(-1, n).astype(np.float64), refp.reshape(-1, n)).max()
+    assert e <= F32_TOL, (n, e)
+    # a Normal-mode family (tabulated spectrum) and the forward entry point at an awkward length
+    mh = make(nw, "mexicanhat", dict(sfreq=1000), dtype="float64").cwt(x[0], fr)
+    assert peak_rel_err(mh, orc.cwt(orc.Family("mexicanhat", sfreq=1000), x[0], fr)).max() <= F64_TOL
+
+
+def test_too_long_raises(nw):
+    from ninwavelets_b200 import _backend as be
+    with pytest.raises(be.BackendError):
+        be.Plan(device=0, dtype=np.float32, family=be.MORSE, interpolate=False, n=(1 << 31) + 7, sfreq=1000.0,
+                freqs=[1.0, 2.0], p0=17.5, p1=3.0)
