@@ -67,7 +67,16 @@ template <> struct StaticPlan<13> { static const int P = 1024, R0 = 16, R1 = 16,
 template <> struct StaticPlan<14> { static const int P = 2048, R0 = 16, R1 = 16, R2 = 8, TPS = 1; };
 template <> struct StaticPlan<15> { static const int P = 4096, R0 = 16, R1 = 16, R2 = 16, TPS = 0; };
 template <> struct StaticPlan<16> { static const int P = 4096, R0 = 16, R1 = 16, R2 = 16, TPS = 1; };
-static const int N_STATIC_PLANS = 16;
+// decimated lengths of resampled rows (N = 600 000 / D splits into 100, 120, 150 x 125 ... 1000): two-pass column
+// transforms and three-pass row transforms of the short factors
+template <> struct StaticPlan<20> { static const int P = 100, R0 = 10, R1 = 10, R2 = 1, TPS = 2; };
+template <> struct StaticPlan<21> { static const int P = 120, R0 = 12, R1 = 10, R2 = 1, TPS = 2; };
+template <> struct StaticPlan<22> { static const int P = 150, R0 = 10, R1 = 15, R2 = 1, TPS = 2; };
+template <> struct StaticPlan<23> { static const int P = 500, R0 = 10, R1 = 10, R2 = 5, TPS = 2; };
+template <> struct StaticPlan<24> { static const int P = 250, R0 = 10, R1 = 5, R2 = 5, TPS = 2; };
+template <> struct StaticPlan<25> { static const int P = 125, R0 = 5, R1 = 5, R2 = 5, TPS = 2; };
+template <> struct StaticPlan<26> { static const int P = 200, R0 = 10, R1 = 10, R2 = 2, TPS = 2; };
+static const int N_STATIC_PLANS = 26;
 template <int ID> NW_HD bool static_plan_matches(const Fft2Plan& st, int tpsh) {
     typedef StaticPlan<ID> S;
     if (st.P != S::P || tpsh != S::TPS) return false;
@@ -88,6 +97,13 @@ inline int static_plan_id(const Fft2Plan& st, int tpsh) {
     if (static_plan_matches<14>(st, tpsh)) return 14;
     if (static_plan_matches<15>(st, tpsh)) return 15;
     if (static_plan_matches<16>(st, tpsh)) return 16;
+    if (static_plan_matches<20>(st, tpsh)) return 20;
+    if (static_plan_matches<21>(st, tpsh)) return 21;
+    if (static_plan_matches<22>(st, tpsh)) return 22;
+    if (static_plan_matches<23>(st, tpsh)) return 23;
+    if (static_plan_matches<24>(st, tpsh)) return 24;
+    if (static_plan_matches<25>(st, tpsh)) return 25;
+    if (static_plan_matches<26>(st, tpsh)) return 26;
     return 0;
 }
 

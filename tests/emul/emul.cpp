@@ -198,6 +198,9 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup
                 } else {
                     if (spA == 2) passA2_body<T, 2>(Q, smp, x, y, t, ntA);
                     else if (spA == 4) passA2_body<T, 4>(Q, smp, x, y, t, ntA);
+                    else if (spA == 20) passA2_body<T, 20>(Q, smp, x, y, t, ntA);
+                    else if (spA == 21) passA2_body<T, 21>(Q, smp, x, y, t, ntA);
+                    else if (spA == 22) passA2_body<T, 22>(Q, smp, x, y, t, ntA);
                     else passA2_body<T, 0>(Q, smp, x, y, t, ntA);
                 }
             });
@@ -205,7 +208,14 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup
             Fibers::get().run(ntB, [&](int t) {
                 if (omode == OUT_POWER) { if (spB == 1) passB2_body<T, OUT_POWER, 1>(Q, smp, x, y, t, ntB); else if (spB == 4) passB2_body<T, OUT_POWER, 4>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_POWER, 0>(Q, smp, x, y, t, ntB); }
                 else if (omode == OUT_ABS) passB2_body<T, OUT_ABS, 0>(Q, smp, x, y, t, ntB);
-                else { if (spB == 1) passB2_body<T, OUT_CWT, 1>(Q, smp, x, y, t, ntB); else passB2_body<T, OUT_CWT, 0>(Q, smp, x, y, t, ntB); }
+                else {
+                    if (spB == 1) passB2_body<T, OUT_CWT, 1>(Q, smp, x, y, t, ntB);
+                    else if (spB == 23) passB2_body<T, OUT_CWT, 23>(Q, smp, x, y, t, ntB);
+                    else if (spB == 24) passB2_body<T, OUT_CWT, 24>(Q, smp, x, y, t, ntB);
+                    else if (spB == 25) passB2_body<T, OUT_CWT, 25>(Q, smp, x, y, t, ntB);
+                    else if (spB == 26) passB2_body<T, OUT_CWT, 26>(Q, smp, x, y, t, ntB);
+                    else passB2_body<T, OUT_CWT, 0>(Q, smp, x, y, t, ntB);
+                }
             });
         if (D > 1) {
             R.y = Y.data(); R.row0 = (int)r0;

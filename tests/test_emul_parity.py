@@ -198,3 +198,18 @@ def test_emul_resampling_is_planned_and_bounded(monkeypatch):
     tight = be.Plan(device=0, dtype=np.float64, family=be.MORSE, interpolate=False, n=600000, sfreq=1000.0,
                     freqs=np.arange(1, 101.0), p0=17.5, p1=3.0)
     assert all(x["err"] <= 5e-14 for x in tight.info()["groups"])
+
+
+def test_emul_resampled_rows_at_cfg2_length():
+    """BASELINE.json config-2 row length (N = 600 000) through the emulation: the decimated lengths 600 000 / D and their
+    compile-time plans (100, 120, 150 x 125 ... 1000; nw_kernels2.cuh StaticPlan 20-26), the vector interpolation kernel
+    in its persistent form, fp32 power against the oracle, every row relative to itself."""
+    rng = np.random.default_rng(5)
+    n = 600000
+    fam = orc.Family("morse", sfreq=1000.0)
+    freqs = np.array([3., 14., 33., 52., 71., 100.])
+    x = rng.standard_normal((1, n)).astype(np.float32)
+    ref = orc.power(fam, x[0].astype(np.float64), freqs)
+    p = emul_transform(desc_from_oracle_family(fam, freqs, n, dtype=0), x, output=2)
+    e = l2_rel_err(p[0], ref)
+    assert e.max() <= F32_TOL, e
