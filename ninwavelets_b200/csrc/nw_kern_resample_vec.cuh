@@ -12,6 +12,13 @@ __global__ void __launch_bounds__(RSV_THREADS, rsv_min_ctas(K, R, PQ)) nwcwt_res
     resample_vec_body<T, K, R, PQ, MODE>(P, nw_smem, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);
 }
 
+template <typename T, int K, int R, int PQ, int MODE>
+__global__ void __launch_bounds__(RSV_THREADS, 4) nwcwt_resample_dir_kernel(const __grid_constant__ ResampleParams<T> P) {
+    __shared__ __align__(16) cx<T> strip[(RSV_THREADS / 32) * RsDirGeo<K, R>::DEPTH * RsDirGeo<K, R>::SLOTS];
+    resample_dir_body<T, K, R, PQ, MODE>(P, (char*)strip, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);
+}
+
+#define NW_RSD_RUN(k) case k: nwcwt_resample_dir_kernel<NW_REAL, k, rs_dir_run(k), NW_RSV_PQ, NW_RSV_MODE><<<grid, RSV_THREADS, 0, s>>>(P); return cudaGetLastError();
 #define NW_RSV_K(k, r) nwcwt_resample_vec_kernel<NW_REAL, k, r, NW_RSV_PQ, NW_RSV_MODE>
 #define NW_RSV_PREP1(k, r) \
     { cudaError_t e = cudaFuncSetAttribute(NW_RSV_K(k, r), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); if (e != cudaSuccess) return e; }
@@ -33,6 +40,13 @@ template <>
 cudaError_t launch_resample_vec<NW_REAL, NW_RSV_PQ, NW_RSV_MODE>(int K, int R, const ResampleParams<NW_REAL>& P, dim3 grid, size_t smem, cudaStream_t s) {
     switch (K) {
         NW_RSV_TAPS(NW_RSV_RUN)
+        default: return cudaErrorInvalidValue;
+    }
+}
+template <>
+cudaError_t launch_resample_dir<NW_REAL, NW_RSV_PQ, NW_RSV_MODE>(int K, const ResampleParams<NW_REAL>& P, dim3 grid, cudaStream_t s) {
+    switch (K) {
+        NW_RSV_TAPS(NW_RSD_RUN)
         default: return cudaErrorInvalidValue;
     }
 }

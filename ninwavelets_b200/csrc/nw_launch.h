@@ -45,4 +45,7 @@ template <typename T, int PQ, int MODE> cudaError_t prepare_resample_vec();
 template <typename T, int PQ, int MODE> bool has_resample_vec(int K);
 template <typename T, int PQ, int MODE>
 cudaError_t launch_resample_vec(int K, int R, const ResampleParams<T>& P, dim3 grid, size_t smem, cudaStream_t s);
+// direct interpolation kernel (nw_resample.cuh: resample_dir_body): no shared memory, run length 8 (K <= 8) or 4
+template <typename T, int PQ, int MODE>
+cudaError_t launch_resample_dir(int K, const ResampleParams<T>& P, dim3 grid, cudaStream_t s);
 }  // namespace nw

@@ -17,6 +17,7 @@
 //                   tile[32 WR][RS]     results (aliases ys: all windows are in registers before the first store);
 //                                       RS = R D (+1 if even) keeps the per-lane stores conflict free.
 #pragma once
+#include <string.h>
 #include "nw_common.h"
 #include "nw_pk.cuh"
 #include "nw_kernels.cuh"
@@ -42,6 +43,8 @@ struct ResampleParams {
     const T* coefq;        // vector kernel: weights regrouped [D / PQ][K][PQ]
     fastdiv dGT;           // vector kernel: x / (work items per row = ceil(M / (32 R)))
     int nrows;             // vector kernel: rows of this launch
+    int G, MW;             // direct kernel: lanes per output sample m (phase groups D / PQ), samples m a warp handles side by side
+    fastdiv dG, dF;        // direct kernel: lane / G, row / F
 };
 
 template <typename T, int K, int R> struct ResampleGeo {
@@ -165,6 +168,11 @@ NW_D void rs_st_shared(double* p, const RsVec<double, 2>& r) { *(double2*)p = ma
 NW_D void rs_copy_out(float* g, const float* s, RsVec<float, 4>*) { __stcs((float4*)g, *(const float4*)s); }
 NW_D void rs_copy_out(float* g, const float* s, RsVec<float, 2>*) { __stcs((float2*)g, *(const float2*)s); }
 NW_D void rs_copy_out(double* g, const double* s, RsVec<double, 2>*) { __stcs((double2*)g, *(const double2*)s); }
+NW_D cx<float> rs_ld_sample(const cx<float>* p) { const float2 v = __ldg((const float2*)p); return mk<float>(v.x, v.y); }
+NW_D cx<double> rs_ld_sample(const cx<double>* p) { const double2 v = __ldg((const double2*)p); return mk<double>(v.x, v.y); }
+NW_D void rs_st_out(float* g, const RsVec<float, 4>& r) { __stcs((float4*)g, make_float4(r.v[0], r.v[1], r.v[2], r.v[3])); }
+NW_D void rs_st_out(float* g, const RsVec<float, 2>& r) { __stcs((float2*)g, make_float2(r.v[0], r.v[1])); }
+NW_D void rs_st_out(double* g, const RsVec<double, 2>& r) { __stcs((double2*)g, make_double2(r.v[0], r.v[1])); }
 template <typename T, int PQ> NW_D RsVec<T, PQ> rs_ld_coef(const T* p);
 template <> NW_D RsVec<float, 4> rs_ld_coef<float, 4>(const float* p) {
     const float4 v = __ldg((const float4*)p);
@@ -219,6 +227,8 @@ NW_D void rs_pair(const cx<double>* w, const double* c0, int cstride, double& o0
 template <typename T, int PQ> inline RsVec<T, PQ> rs_ld_coef(const T* p) { RsVec<T, PQ> r; for (int j = 0; j < PQ; ++j) r.v[j] = p[j]; return r; }
 template <typename T, int PQ> inline void rs_st_shared(T* p, const RsVec<T, PQ>& r) { for (int j = 0; j < PQ; ++j) p[j] = r.v[j]; }
 template <typename T, int PQ> inline void rs_copy_out(T* g, const T* s, RsVec<T, PQ>*) { for (int j = 0; j < PQ; ++j) g[j] = s[j]; }
+template <typename T> inline cx<T> rs_ld_sample(const cx<T>* p) { return *p; }
+template <typename T, int PQ> inline void rs_st_out(T* g, const RsVec<T, PQ>& r) { for (int j = 0; j < PQ; ++j) g[j] = r.v[j]; }
 template <int K, int MODE, typename T>
 inline void rs_pair(const cx<T>* w, const T* c0, int cstride, T& o0, T& o1) {
     T r0 = 0, i0 = 0, r1 = 0, i1 = 0;
@@ -357,6 +367,202 @@ NW_HD void resample_vec_body(const ResampleParams<T>& P, char* smem, int bx, int
         }
         rs_group_sync(wr, WP, WR);   // the tile is read: the next item's samples may overwrite it
     }
+}
+
+// ---- direct kernel ------------------------------------------------------------------------------------------
+// The interpolation with its results leaving straight from registers in stores that are already coalesced: no output
+// staging, no CTA barrier.
+//   * lane = j G + g: phase group g (PQ neighbouring phases, G = D / PQ groups) of the run j of R consecutive m; the
+//     MW = 32 / G runs of a warp are consecutive, so a warp-item is MW R consecutive m of one row = MW R D outputs.
+//     A lane's phase group never changes: its PQ K weights are loaded ONCE per kernel and stay in registers.
+//   * the MW R + K - 1 samples of an item - one contiguous piece of the decimated row - are copied by the warp into its
+//     own shared-memory strip with 16-byte asynchronous copies (LDGSTS), double buffered: the copy of the next item is
+//     in flight during the arithmetic of the current one.  R is ODD, so the per-lane window loads (lane stride R
+//     samples = 8 R bytes) are bank-conflict free on the linear strip.  (Per-lane loads of the windows straight from
+//     global memory cost one L1 sector access per run and sample and bound the first version of this kernel at 83 % L1
+//     throughput; staging through registers and a padded strip doubled its instruction count: profiles/r02.)
+//   * the inner loop is the K packed FMAs per output pair of resample_vec_body (rs_pair);
+//   * the PQ outputs of (m, g) are one 16-byte (8-byte) streaming store; the G lanes of a run cover the D consecutive
+//     outputs of m, so every store instruction of a warp writes MW whole pieces of 4 D bytes, and the R stores of a
+//     lane fill its run's R D outputs back to back.
+//   * warps are independent (persistent, striding over the items; one warp-level barrier per item); item -> (row,
+//     piece) is carried incrementally, without divisions.
+template <int K, int R> struct RsDirGeo {
+    static const int SLOTS = (32 * R + K + 2 + 1) / 2 * 2;  // strip of a warp, in samples (MW = 32, one alignment sample each side)
+    static const int DEPTH = 4;                             // strips per warp: the copies run DEPTH - 1 items ahead
+};
+#if defined(__CUDA_ARCH__)
+#define NW_WARP_SYNC() __syncwarp()
+NW_D void rs_cp16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+NW_D void rs_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> NW_D void rs_cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#else
+#define NW_WARP_SYNC() NW_SYNC()
+inline void rs_cp16(void* dst, const void* src) { memcpy(dst, src, 16); }
+inline void rs_cp_commit() {}
+template <int N> inline void rs_cp_wait() {}
+#endif
+template <typename T, int K, int R, int PQ, int MODE>
+NW_HD void resample_dir_body(const ResampleParams<T>& P, char* smem, int bx, int nbx, int tid, int nthr) {
+    static_assert((K & 1) == 0 && (R & 1) == 1 && (PQ == 2 || PQ == 4), "even taps, odd runs");
+    typedef RsDirGeo<K, R> GEO;
+    const int M = P.M, D = P.D, G = P.G, MW = P.MW;
+    const int lane = tid & 31, warp = tid >> 5, wpc = nthr >> 5;
+    const int j = (int)fd_div((uint32_t)lane, P.dG), g = lane - j * G;
+    const bool act = j < MW;                                // 32 - MW G idle lanes when G does not divide 32
+    cx<T>* strip = (cx<T>*)smem + (size_t)warp * (GEO::DEPTH * GEO::SLOTS);
+    RsVec<T, PQ> c[K];
+    {
+        const T* cq = P.coefq + (size_t)(act ? g : 0) * (K * PQ);
+#pragma unroll
+        for (int t = 0; t < K; ++t) c[t] = rs_ld_coef<T, PQ>(cq + t * PQ);
+    }
+    const int GT = (int)P.dGT.d;                            // items per row
+    const int CW = MW * R, NS = CW + K - 1;                 // m per item, samples an item needs
+    // every warp owns a CONTIGUOUS range of items (consecutive pieces of consecutive rows): pointers are set up once per
+    // row and advance by constants - the item loop carries no divisions, no table look-ups and no 64-bit multiplies
+    const uint32_t total = (uint32_t)GT * (uint32_t)P.nrows;
+    const uint32_t nwarps = (uint32_t)nbx * (uint32_t)wpc;
+    const uint32_t per = (total + nwarps - 1) / nwarps;     // trip count, uniform over the grid (host emulation: CTA barriers)
+    const uint32_t i0 = ((uint32_t)bx * (uint32_t)wpc + (uint32_t)warp) * per;
+    const int cnt = i0 >= total ? 0 : (int)(total - i0 < per ? total - i0 : per);   // items of this warp
+    // an item whose samples lie inside the row, with one spare sample either side, is copied in aligned 16-byte pieces;
+    // the first and the last one or two items of a row are copied sample by sample, wrapped
+    const int gt_fast = (M - NS - K / 2) / CW;              // gt <= gt_fast: gt CW + 1 - K / 2 + NS + 1 <= M
+    const int by0 = (int)(i0 / (uint32_t)GT), gt0 = (int)(i0 - (uint32_t)by0 * (uint32_t)GT);
+    // fetch cursor: DEPTH - 1 items ahead of the consume cursor
+    int pgt = gt0, pleft = cnt;
+    const cx<T>* psrc = P.y + (size_t)by0 * (size_t)P.ystride + ((long long)gt0 * CW + 1 - K / 2);   // sample b of the item
+    cx<T>* const ring0 = strip;
+    cx<T>* const ring1 = strip + GEO::DEPTH * GEO::SLOTS;
+    cx<T>* pdst = ring0;
+    auto issue = [&]() {
+        if (pleft > 0) {
+#ifdef RS_EXP_NOLOAD   // timing experiment: no sample loads
+            if (pgt == -12345) {
+#endif
+            if (pgt >= 1 && pgt <= gt_fast) {
+                const int a = (int)(((uintptr_t)psrc / sizeof(cx<T>)) & 1);
+                const cx<T>* src = psrc - a + 2 * lane;
+                cx<T>* dst = pdst + 2 * lane;
+                const int n16 = (NS + a + 1) >> 1;
+                if (lane < n16) rs_cp16(dst, src);
+                if (lane + 32 < n16) rs_cp16(dst + 64, src + 64);
+                for (int u = lane + 64; u < n16; u += 32) rs_cp16(dst + 2 * (u - lane), src + 2 * (u - lane));
+            } else {
+                const cx<T>* y = psrc - ((long long)pgt * CW + 1 - K / 2);   // row start
+                const int b = pgt * CW + 1 - K / 2;
+                for (int i = lane; i < NS; i += 32) {
+                    int mi = b + i;
+                    if (mi < 0) mi += M;
+                    if (mi >= M) mi -= M;                   // M >= NS (resample_dir_shape)
+                    pdst[i] = y[mi];
+                }
+            }
+#ifdef RS_EXP_NOLOAD
+            }
+#endif
+        }
+        rs_cp_commit();
+        --pleft;
+        psrc += CW;
+        if (++pgt == GT) { pgt = 0; psrc += P.ystride - (long long)GT * CW; }
+        pdst += GEO::SLOTS;
+        if (pdst == ring1) pdst = ring0;
+    };
+#pragma unroll 1
+    for (int d = 0; d < GEO::DEPTH - 1; ++d) issue();
+    // consume cursor
+    int gt = gt0, by = by0;
+    const cx<T>* csrc = P.y + (size_t)by0 * (size_t)P.ystride + ((long long)gt0 * CW + 1 - K / 2);
+    const cx<T>* cstrip = ring0 + (act ? j : 0) * R;
+    const int lane_off = (act ? j : 0) * R;
+    T* o = nullptr;                                         // output of (first m of this lane's run in the item, phase group g)
+    bool new_row = true;
+    const size_t ostep = (size_t)CW * (size_t)D;
+    for (uint32_t k = 0; k < per; ++k) {
+        rs_cp_wait<GEO::DEPTH - 2>();                       // all but the DEPTH - 2 most recent copies have landed
+        NW_WARP_SYNC();                                     // ... for every lane; and the strip read DEPTH - 1 items ago is free
+        issue();
+        if ((int)k >= cnt) continue;
+        if (new_row) {                                      // output row through the group's frequency map
+            const int gr = P.row0 + by, si = gr / P.F, fi = gr - si * P.F;
+            o = (T*)P.out + ((size_t)si * (size_t)P.F_out + (size_t)(P.fmap ? P.fmap[fi] : fi)) * (size_t)P.N +
+                ((size_t)gt * (size_t)CW + (size_t)lane_off) * (size_t)D + (size_t)(g * PQ);
+            new_row = false;
+        }
+        const bool fast = gt >= 1 && gt <= gt_fast;
+        const int a0 = fast ? (int)(((uintptr_t)csrc / sizeof(cx<T>)) & 1) : 0;
+        cx<T> w[R + K - 1];
+        {
+            const cx<T>* yb = cstrip + a0;
+#pragma unroll
+            for (int q = 0; q < R + K - 1; ++q) w[q] = yb[q];
+        }
+        const bool full = gt < GT - 1;                      // every run of the item lies inside the row
+        const int left = M - (gt * CW + lane_off);
+        T* const oc = o;
+        o += ostep;
+        csrc += CW;
+        if (++gt == GT) { gt = 0; ++by; csrc += P.ystride - (long long)GT * CW; new_row = true; }
+        cstrip += GEO::SLOTS;
+        if (cstrip >= ring1) cstrip -= GEO::DEPTH * GEO::SLOTS;
+        if (!act) continue;
+        if (full) {                                         // straight-line: the chains of neighbouring m interleave
+#pragma unroll
+            for (int mm = 0; mm < R; ++mm) {
+                RsVec<T, PQ> r;
+#pragma unroll
+#ifdef RS_EXP_NOFMA   // timing experiment: one multiply per output instead of the K taps
+                for (int q = 0; q < PQ; ++q) r.v[q] = w[mm + (q & 1)].x * c[q & 1].v[q];
+#else
+                for (int q = 0; q < PQ; q += 2) rs_pair<K, MODE>(w + mm, &c[0].v[q], PQ, r.v[q], r.v[q + 1]);
+#endif
+#ifdef RS_EXP_NOST    // timing experiment: results are computed but (almost) never stored
+                if (r.v[0] == (T)123.456) rs_st_out(oc + (size_t)mm * (size_t)D, r);
+#else
+                rs_st_out(oc + (size_t)mm * (size_t)D, r);
+#endif
+            }
+        } else {                                            // the row ends inside this item
+#pragma unroll
+            for (int mm = 0; mm < R; ++mm) {
+                RsVec<T, PQ> r;
+#pragma unroll
+                for (int q = 0; q < PQ; q += 2) rs_pair<K, MODE>(w + mm, &c[0].v[q], PQ, r.v[q], r.v[q + 1]);
+                if (mm < left) rs_st_out(oc + (size_t)mm * (size_t)D, r);
+            }
+        }
+    }
+}
+
+// host-side launch geometry of the direct kernel for a group (D, K) at decimated length M; false: not eligible
+struct ResampleDirShape { int R, PQ, G, MW, nthr, ctas_per_sm; unsigned items; size_t smem; };
+constexpr int rs_dir_run(int K) { return K <= 8 ? 7 : 5; }   // odd: conflict-free window loads; window 2 (R + K - 1) + weights PQ K registers
+template <typename T> inline bool resample_dir_shape(int D, int K, long long M, long long rows, int F, ResampleDirShape& v) {
+    if (sizeof(T) != 4 || (D & 1) || (K & 1) || K < 4 || K > 12) return false;
+    v.PQ = (D & 3) ? 2 : 4;
+    v.G = D / v.PQ;
+    if (v.G > 32) return false;
+    v.MW = 32 / v.G;
+    v.R = rs_dir_run(K);
+    if (M < (long long)v.MW * v.R + K + 2) return false;   // an item's samples never wrap twice
+    if ((rows + 1) * (long long)F >= (1LL << 32)) return false;   // fastdiv of the row index by F
+    v.nthr = 128;
+    v.ctas_per_sm = 4;
+    v.smem = (size_t)(v.nthr / 32) * 4 * (size_t)((32 * v.R + K + 2 + 1) / 2 * 2) * 2 * sizeof(T);   // RsDirGeo::DEPTH strips per warp
+    const long long cw = (long long)v.MW * v.R;
+    v.items = (unsigned)((M + cw - 1) / cw);
+    if ((long long)v.items * rows >= (1LL << 31)) return false;
+    return true;
+}
+inline unsigned resample_dir_grid(const ResampleDirShape& v, long long rows, int sms) {
+    const long long wpc = v.nthr / 32;
+    const long long ctas = ((long long)v.items * rows + wpc - 1) / wpc;
+    const long long cap = (long long)sms * v.ctas_per_sm;
+    return (unsigned)(ctas < cap ? ctas : cap);
 }
 
 // resident CTAs per SM the vector kernel's register budget is sized for (__launch_bounds__): window 2 (R + K - 1),

@@ -320,6 +320,7 @@ template <> struct Long2Dispatch<double> {
 template <typename T> struct RsVecDispatch {
     static cudaError_t prepare() { return cudaSuccess; }
     static cudaError_t run(int, int, int, int, const ResampleParams<T>&, dim3, size_t, cudaStream_t) { return cudaErrorInvalidValue; }
+    static cudaError_t run_dir(int, int, int, const ResampleParams<T>&, dim3, cudaStream_t) { return cudaErrorInvalidValue; }
 };
 template <> struct RsVecDispatch<float> {
     static cudaError_t prepare() {
@@ -335,7 +336,14 @@ template <> struct RsVecDispatch<float> {
         return mode == OUT_POWER ? launch_resample_vec<float, 2, OUT_POWER>(K, R, P, g, sm, s)
                                  : launch_resample_vec<float, 2, OUT_ABS>(K, R, P, g, sm, s);
     }
+    static cudaError_t run_dir(int PQ, int mode, int K, const ResampleParams<float>& P, dim3 g, cudaStream_t s) {
+        if (PQ == 4) return mode == OUT_POWER ? launch_resample_dir<float, 4, OUT_POWER>(K, P, g, s)
+                                              : launch_resample_dir<float, 4, OUT_ABS>(K, P, g, s);
+        return mode == OUT_POWER ? launch_resample_dir<float, 2, OUT_POWER>(K, P, g, s)
+                                 : launch_resample_dir<float, 2, OUT_ABS>(K, P, g, s);
+    }
 };
+static bool g_rs_dir = !(getenv("NWCWT_RS_DIR") && atoi(getenv("NWCWT_RS_DIR")) == 0);   // A/B switch of the interpolation kernels
 
 template <typename T>
 static int upload_tw(void** dptr, long long count, long long P, long long step) {
@@ -777,9 +785,11 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
     ResampleParams<T> R;
     ResampleShape shp{1, 1, 0, 0, 0};
     ResampleVecShape vshp;
-    bool vec = false;
+    ResampleDirShape dshp;
+    bool vec = false, dir = false;
     if (D > 1) {
         vec = resample_vec_shape<T>(D, mg->K, eh.N, vshp) && dg->d_coefq;
+        dir = vec && g_rs_dir && resample_dir_shape<T>(D, mg->K, eh.N, rows, eh.F, dshp) && dshp.PQ == vshp.PQ;
         shp = resample_shape<T>(D, mg->K);
         memset(&R, 0, sizeof(R));
         R.ystride = eh.N;
@@ -798,6 +808,7 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
         R.RS = shp.RS;
         R.dRD = make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
         if (vec) { R.WR = vshp.WR; R.WP = vshp.WP; R.RS = (int)vshp.gbytes; R.dRD = vshp.dRD; R.dGT = make_fastdiv(vshp.items); R.dGT.d = vshp.items; }
+        if (dir) { R.G = dshp.G; R.MW = dshp.MW; R.dG = make_fastdiv((uint32_t)dshp.G); R.dF = make_fastdiv((uint32_t)eh.F); R.dGT = make_fastdiv(dshp.items); R.dGT.d = dshp.items; }
         R.coefq = (const T*)dg->d_coefq;
         Q.eq = (const T*)dg->d_eq;
         Q.out_mode = NWCWT_OUT_CWT;
@@ -826,7 +837,8 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
             const unsigned tiles = (unsigned)((eh.N + shp.C - 1) / shp.C);
             LaunchScope ls(6, st);
             R.nrows = g;
-            if (vec) CUDA_TRY(RsVecDispatch<T>::run(vshp.PQ, output, mg->K, vshp.R, R, dim3(resample_vec_grid(vshp, g, device_sms(hp.device))), vshp.smem, st));
+            if (dir) CUDA_TRY(RsVecDispatch<T>::run_dir(dshp.PQ, output, mg->K, R, dim3(resample_dir_grid(dshp, g, device_sms(hp.device))), st));
+            else if (vec) CUDA_TRY(RsVecDispatch<T>::run(vshp.PQ, output, mg->K, vshp.R, R, dim3(resample_vec_grid(vshp, g, device_sms(hp.device))), vshp.smem, st));
             else CUDA_TRY(launch_resample<T>(mg->K, output, R, dim3(tiles, g), 32 * shp.WR * shp.WP, shp.smem, st));
         }
     }

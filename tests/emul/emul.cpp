@@ -122,6 +122,20 @@ static void resample_vec_launch(ResampleParams<T> R, int mode, char* smp, const 
         });
 }
 
+template <typename T, int K, int PQ>
+static void resample_dir_launch(ResampleParams<T> R, int mode, const ResampleDirShape& v, int g) {
+    R.nrows = g;
+    const int nbx = (int)std::min<unsigned>(resample_dir_grid(v, g, 1), 3u);   // a small persistent grid: every warp loops
+    constexpr int RR = rs_dir_run(K);
+    std::vector<char> strip(v.smem + 64);
+    char* sp = (char*)(((uintptr_t)strip.data() + 31) & ~(uintptr_t)31);
+    for (int x = 0; x < nbx; ++x)
+        Fibers::get().run(v.nthr, [&](int t) {   // warp-level synchronisation is emulated by CTA barriers
+            if (mode == OUT_POWER) resample_dir_body<T, K, RR, PQ, OUT_POWER>(R, sp, x, nbx, t, v.nthr);
+            else resample_dir_body<T, K, RR, PQ, OUT_ABS>(R, sp, x, nbx, t, v.nthr);
+        });
+}
+
 // Inverse transforms of gs signals x the frequencies of plan eh (the main plan, or the sub-plan of group mg) on the
 // packed kernels, followed by the interpolation kernel for a resampled group: mirrors nwcwt.cu: inverse_rows.
 template <typename T>
@@ -153,11 +167,13 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup
     ResampleParams<T> R;
     ResampleShape shp{1, 1, 0, 0, 0};
     ResampleVecShape vshp;
-    bool vec = false;
+    ResampleDirShape dshp;
+    bool vec = false, dir = false;
     std::vector<T> coefq;
     memset(&R, 0, sizeof(R));
     if (D > 1) {
         vec = resample_vec_shape<T>(D, mg->K, eh.N, vshp);
+        dir = vec && !(g_mode & 512) && resample_dir_shape<T>(D, mg->K, eh.N, (long long)gs * eh.F, eh.F, dshp) && dshp.PQ == vshp.PQ;
         eq.assign(mg->eq.begin(), mg->eq.end());
         coef.assign(mg->coef.begin(), mg->coef.end());
         Y.resize((size_t)ring2 * eh.N);
@@ -171,6 +187,7 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup
             resample_coefq<T>(mg->coef.data(), D, mg->K, vshp.PQ, coefq.data());
             R.coefq = coefq.data();
             R.WR = vshp.WR; R.WP = vshp.WP; R.RS = (int)vshp.gbytes; R.dRD = vshp.dRD; R.dGT = make_fastdiv(vshp.items); R.dGT.d = vshp.items;
+            if (dir) { R.G = dshp.G; R.MW = dshp.MW; R.dG = make_fastdiv((uint32_t)dshp.G); R.dF = make_fastdiv((uint32_t)eh.F); R.dGT = make_fastdiv(dshp.items); R.dGT.d = dshp.items; }
         }
         Q.eq = eq.data();
         Q.out_mode = OUT_CWT;
@@ -220,7 +237,15 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup
         if (D > 1) {
             R.y = Y.data(); R.row0 = (int)r0;
             const int tiles = (int)((eh.N + shp.C - 1) / shp.C), nt = 32 * shp.WR * shp.WP;
-            if (vec) {
+            if (dir) {
+                switch (mg->K * 10 + dshp.PQ) {
+#define RD_CASE(k) case k * 10 + 4: resample_dir_launch<T, k, 4>(R, output, dshp, g); break; \
+                   case k * 10 + 2: resample_dir_launch<T, k, 2>(R, output, dshp, g); break;
+                    RD_CASE(4) RD_CASE(6) RD_CASE(8) RD_CASE(10) RD_CASE(12)
+#undef RD_CASE
+                    default: return -2;
+                }
+            } else if (vec) {
                 switch (mg->K * 10 + vshp.PQ) {
 #define RV_CASE(k) case k * 10 + 4: resample_vec_launch<T, k, 4>(R, output, smp, vshp, g); break; \
                    case k * 10 + 2: resample_vec_launch<T, k, 2>(R, output, smp, vshp, g); break;
