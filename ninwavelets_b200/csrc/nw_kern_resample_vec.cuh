@@ -12,8 +12,11 @@ __global__ void __launch_bounds__(RSV_THREADS, rsv_min_ctas(K, R, PQ)) nwcwt_res
     resample_vec_body<T, K, R, PQ, MODE>(P, nw_smem, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);
 }
 
+#ifndef RSD_MINCTAS
+#define RSD_MINCTAS 4
+#endif
 template <typename T, int K, int R, int PQ, int MODE>
-__global__ void __launch_bounds__(RSV_THREADS, 4) nwcwt_resample_dir_kernel(const __grid_constant__ ResampleParams<T> P) {
+__global__ void __launch_bounds__(RSV_THREADS, RSD_MINCTAS) nwcwt_resample_dir_kernel(const __grid_constant__ ResampleParams<T> P) {
     __shared__ __align__(16) cx<T> strip[(RSV_THREADS / 32) * RsDirGeo<K, R>::DEPTH * RsDirGeo<K, R>::SLOTS];
     resample_dir_body<T, K, R, PQ, MODE>(P, (char*)strip, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);
 }

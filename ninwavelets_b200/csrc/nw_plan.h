@@ -938,7 +938,12 @@ inline bool build_weight_table(HostPlan& hp, const double* eq, size_t max_bytes,
 // its own length; interpolation = fir0 + fir_tap K with the vector kernel (even D), firs0 + firs_tap K with the scalar one
 struct MrCost { double engine, fir0, fir_tap, firs0, firs_tap; };
 inline MrCost mr_cost(int dtype) {
-    return dtype == 0 ? MrCost{8.0, 0.55, 0.035, 1.0, 0.18} : MrCost{20.0, 1.6, 0.3, 1.6, 0.3};
+    MrCost c = dtype == 0 ? MrCost{8.0, 0.55, 0.035, 1.0, 0.18} : MrCost{20.0, 1.6, 0.3, 1.6, 0.3};
+    // tuning overrides (thousandths of a picosecond): NWCWT_COST_ENGINE, NWCWT_COST_FIR0, NWCWT_COST_TAP
+    if (env_int("NWCWT_COST_ENGINE", 0) > 0) c.engine = 0.001 * env_int("NWCWT_COST_ENGINE", 0);
+    if (env_int("NWCWT_COST_FIR0", 0) > 0) c.fir0 = 0.001 * env_int("NWCWT_COST_FIR0", 0);
+    if (env_int("NWCWT_COST_TAP", 0) > 0) c.fir_tap = 0.001 * env_int("NWCWT_COST_TAP", 0);
+    return c;
 }
 // the interpolation kernels a decimation can use: vector kernel (nw_resample.cuh: resample_vec_body) for even D in fp32
 inline bool resample_is_vec(int dtype, int D) { return dtype == 0 && (D & 1) == 0; }

@@ -45,6 +45,7 @@ struct ResampleParams {
     int nrows;             // vector kernel: rows of this launch
     int G, MW;             // direct kernel: lanes per output sample m (phase groups D / PQ), samples m a warp handles side by side
     fastdiv dG, dF;        // direct kernel: lane / G, row / F
+    int NSUB;              // direct kernel: sub-items (MW runs of R samples m side by side) per item
 };
 
 template <typename T, int K, int R> struct ResampleGeo {
@@ -388,8 +389,8 @@ NW_HD void resample_vec_body(const ResampleParams<T>& P, char* smem, int bx, int
 //   * warps are independent (persistent, striding over the items; one warp-level barrier per item); item -> (row,
 //     piece) is carried incrementally, without divisions.
 template <int K, int R> struct RsDirGeo {
-    static const int SLOTS = (32 * R + K + 2 + 1) / 2 * 2;  // strip of a warp, in samples (MW = 32, one alignment sample each side)
-    static const int DEPTH = 4;                             // strips per warp: the copies run DEPTH - 1 items ahead
+    static const int SLOTS = 16 * R * 4 + K + 2 + (K & 1);  // strip of a warp, in samples: 4 sub-items of 16 runs (or 2 of 32), one alignment sample each side
+    static const int DEPTH = 3;                             // strips per warp: the copies run DEPTH - 1 items ahead
 };
 #if defined(__CUDA_ARCH__)
 #define NW_WARP_SYNC() __syncwarp()
@@ -420,7 +421,8 @@ NW_HD void resample_dir_body(const ResampleParams<T>& P, char* smem, int bx, int
         for (int t = 0; t < K; ++t) c[t] = rs_ld_coef<T, PQ>(cq + t * PQ);
     }
     const int GT = (int)P.dGT.d;                            // items per row
-    const int CW = MW * R, NS = CW + K - 1;                 // m per item, samples an item needs
+    const int CW = MW * R;                                  // m per sub-item: the runs of the warp's lanes side by side
+    const int NSUB = P.NSUB, CWI = NSUB * CW, NS = CWI + K - 1;   // sub-items, m and samples per item
     // every warp owns a CONTIGUOUS range of items (consecutive pieces of consecutive rows): pointers are set up once per
     // row and advance by constants - the item loop carries no divisions, no table look-ups and no 64-bit multiplies
     const uint32_t total = (uint32_t)GT * (uint32_t)P.nrows;
@@ -430,11 +432,11 @@ NW_HD void resample_dir_body(const ResampleParams<T>& P, char* smem, int bx, int
     const int cnt = i0 >= total ? 0 : (int)(total - i0 < per ? total - i0 : per);   // items of this warp
     // an item whose samples lie inside the row, with one spare sample either side, is copied in aligned 16-byte pieces;
     // the first and the last one or two items of a row are copied sample by sample, wrapped
-    const int gt_fast = (M - NS - K / 2) / CW;              // gt <= gt_fast: gt CW + 1 - K / 2 + NS + 1 <= M
+    const int gt_fast = (M - NS - K / 2) / CWI;             // gt <= gt_fast: gt CWI + 1 - K / 2 + NS + 1 <= M
     const int by0 = (int)(i0 / (uint32_t)GT), gt0 = (int)(i0 - (uint32_t)by0 * (uint32_t)GT);
     // fetch cursor: DEPTH - 1 items ahead of the consume cursor
     int pgt = gt0, pleft = cnt;
-    const cx<T>* psrc = P.y + (size_t)by0 * (size_t)P.ystride + ((long long)gt0 * CW + 1 - K / 2);   // sample b of the item
+    const cx<T>* psrc = P.y + (size_t)by0 * (size_t)P.ystride + ((long long)gt0 * CWI + 1 - K / 2);   // sample b of the item
     cx<T>* const ring0 = strip;
     cx<T>* const ring1 = strip + GEO::DEPTH * GEO::SLOTS;
     cx<T>* pdst = ring0;
@@ -448,12 +450,11 @@ NW_HD void resample_dir_body(const ResampleParams<T>& P, char* smem, int bx, int
                 const cx<T>* src = psrc - a + 2 * lane;
                 cx<T>* dst = pdst + 2 * lane;
                 const int n16 = (NS + a + 1) >> 1;
-                if (lane < n16) rs_cp16(dst, src);
-                if (lane + 32 < n16) rs_cp16(dst + 64, src + 64);
-                for (int u = lane + 64; u < n16; u += 32) rs_cp16(dst + 2 * (u - lane), src + 2 * (u - lane));
+#pragma unroll 4
+                for (int u = lane; u < n16; u += 32) rs_cp16(dst + 2 * (u - lane), src + 2 * (u - lane));
             } else {
-                const cx<T>* y = psrc - ((long long)pgt * CW + 1 - K / 2);   // row start
-                const int b = pgt * CW + 1 - K / 2;
+                const cx<T>* y = psrc - ((long long)pgt * CWI + 1 - K / 2);   // row start
+                const int b = pgt * CWI + 1 - K / 2;
                 for (int i = lane; i < NS; i += 32) {
                     int mi = b + i;
                     if (mi < 0) mi += M;
@@ -467,8 +468,8 @@ NW_HD void resample_dir_body(const ResampleParams<T>& P, char* smem, int bx, int
         }
         rs_cp_commit();
         --pleft;
-        psrc += CW;
-        if (++pgt == GT) { pgt = 0; psrc += P.ystride - (long long)GT * CW; }
+        psrc += CWI;
+        if (++pgt == GT) { pgt = 0; psrc += P.ystride - (long long)GT * CWI; }
         pdst += GEO::SLOTS;
         if (pdst == ring1) pdst = ring0;
     };
@@ -476,12 +477,12 @@ NW_HD void resample_dir_body(const ResampleParams<T>& P, char* smem, int bx, int
     for (int d = 0; d < GEO::DEPTH - 1; ++d) issue();
     // consume cursor
     int gt = gt0, by = by0;
-    const cx<T>* csrc = P.y + (size_t)by0 * (size_t)P.ystride + ((long long)gt0 * CW + 1 - K / 2);
+    const cx<T>* csrc = P.y + (size_t)by0 * (size_t)P.ystride + ((long long)gt0 * CWI + 1 - K / 2);
     const cx<T>* cstrip = ring0 + (act ? j : 0) * R;
     const int lane_off = (act ? j : 0) * R;
     T* o = nullptr;                                         // output of (first m of this lane's run in the item, phase group g)
     bool new_row = true;
-    const size_t ostep = (size_t)CW * (size_t)D;
+    const size_t ostep = (size_t)CW * (size_t)D;           // outputs per sub-item
     for (uint32_t k = 0; k < per; ++k) {
         rs_cp_wait<GEO::DEPTH - 2>();                       // all but the DEPTH - 2 most recent copies have landed
         NW_WARP_SYNC();                                     // ... for every lane; and the strip read DEPTH - 1 items ago is free
@@ -490,56 +491,56 @@ NW_HD void resample_dir_body(const ResampleParams<T>& P, char* smem, int bx, int
         if (new_row) {                                      // output row through the group's frequency map
             const int gr = P.row0 + by, si = gr / P.F, fi = gr - si * P.F;
             o = (T*)P.out + ((size_t)si * (size_t)P.F_out + (size_t)(P.fmap ? P.fmap[fi] : fi)) * (size_t)P.N +
-                ((size_t)gt * (size_t)CW + (size_t)lane_off) * (size_t)D + (size_t)(g * PQ);
+                ((size_t)gt * (size_t)CWI + (size_t)lane_off) * (size_t)D + (size_t)(g * PQ);
             new_row = false;
         }
         const bool fast = gt >= 1 && gt <= gt_fast;
         const int a0 = fast ? (int)(((uintptr_t)csrc / sizeof(cx<T>)) & 1) : 0;
-        cx<T> w[R + K - 1];
-        {
-            const cx<T>* yb = cstrip + a0;
-#pragma unroll
-            for (int q = 0; q < R + K - 1; ++q) w[q] = yb[q];
-        }
+        const cx<T>* yb = cstrip + a0;
+        int mrun = gt * CWI + lane_off;                     // first m of this lane's run in the sub-item
         const bool full = gt < GT - 1;                      // every run of the item lies inside the row
-        const int left = M - (gt * CW + lane_off);
-        T* const oc = o;
-        o += ostep;
-        csrc += CW;
-        if (++gt == GT) { gt = 0; ++by; csrc += P.ystride - (long long)GT * CW; new_row = true; }
+        csrc += CWI;
+        if (++gt == GT) { gt = 0; ++by; csrc += P.ystride - (long long)GT * CWI; new_row = true; }
         cstrip += GEO::SLOTS;
         if (cstrip >= ring1) cstrip -= GEO::DEPTH * GEO::SLOTS;
-        if (!act) continue;
-        if (full) {                                         // straight-line: the chains of neighbouring m interleave
+#pragma unroll 1
+        for (int sub = 0; sub < NSUB; ++sub, yb += CW, mrun += CW, o += ostep) {
+            if (!act) continue;
+            cx<T> w[R + K - 1];
 #pragma unroll
-            for (int mm = 0; mm < R; ++mm) {
-                RsVec<T, PQ> r;
+            for (int q = 0; q < R + K - 1; ++q) w[q] = yb[q];
+            if (full) {                                     // straight-line: the chains of neighbouring m interleave
+#pragma unroll
+                for (int mm = 0; mm < R; ++mm) {
+                    RsVec<T, PQ> r;
 #pragma unroll
 #ifdef RS_EXP_NOFMA   // timing experiment: one multiply per output instead of the K taps
-                for (int q = 0; q < PQ; ++q) r.v[q] = w[mm + (q & 1)].x * c[q & 1].v[q];
+                    for (int q = 0; q < PQ; ++q) r.v[q] = w[mm + (q & 1)].x * c[q & 1].v[q];
 #else
-                for (int q = 0; q < PQ; q += 2) rs_pair<K, MODE>(w + mm, &c[0].v[q], PQ, r.v[q], r.v[q + 1]);
+                    for (int q = 0; q < PQ; q += 2) rs_pair<K, MODE>(w + mm, &c[0].v[q], PQ, r.v[q], r.v[q + 1]);
 #endif
 #ifdef RS_EXP_NOST    // timing experiment: results are computed but (almost) never stored
-                if (r.v[0] == (T)123.456) rs_st_out(oc + (size_t)mm * (size_t)D, r);
+                    if (r.v[0] == (T)123.456) rs_st_out(o + (size_t)mm * (size_t)D, r);
 #else
-                rs_st_out(oc + (size_t)mm * (size_t)D, r);
+                    rs_st_out(o + (size_t)mm * (size_t)D, r);
 #endif
-            }
-        } else {                                            // the row ends inside this item
+                }
+            } else {                                        // the row ends inside this item
+                const int left = M - mrun;
 #pragma unroll
-            for (int mm = 0; mm < R; ++mm) {
-                RsVec<T, PQ> r;
+                for (int mm = 0; mm < R; ++mm) {
+                    RsVec<T, PQ> r;
 #pragma unroll
-                for (int q = 0; q < PQ; q += 2) rs_pair<K, MODE>(w + mm, &c[0].v[q], PQ, r.v[q], r.v[q + 1]);
-                if (mm < left) rs_st_out(oc + (size_t)mm * (size_t)D, r);
+                    for (int q = 0; q < PQ; q += 2) rs_pair<K, MODE>(w + mm, &c[0].v[q], PQ, r.v[q], r.v[q + 1]);
+                    if (mm < left) rs_st_out(o + (size_t)mm * (size_t)D, r);
+                }
             }
         }
     }
 }
 
 // host-side launch geometry of the direct kernel for a group (D, K) at decimated length M; false: not eligible
-struct ResampleDirShape { int R, PQ, G, MW, nthr, ctas_per_sm; unsigned items; size_t smem; };
+struct ResampleDirShape { int R, PQ, G, MW, NSUB, nthr, ctas_per_sm; unsigned items; size_t smem; };
 constexpr int rs_dir_run(int K) { return K <= 8 ? 7 : 5; }   // odd: conflict-free window loads; window 2 (R + K - 1) + weights PQ K registers
 template <typename T> inline bool resample_dir_shape(int D, int K, long long M, long long rows, int F, ResampleDirShape& v) {
     if (sizeof(T) != 4 || (D & 1) || (K & 1) || K < 4 || K > 12) return false;
@@ -552,8 +553,12 @@ template <typename T> inline bool resample_dir_shape(int D, int K, long long M, 
     if ((rows + 1) * (long long)F >= (1LL << 32)) return false;   // fastdiv of the row index by F
     v.nthr = 128;
     v.ctas_per_sm = 4;
-    v.smem = (size_t)(v.nthr / 32) * 4 * (size_t)((32 * v.R + K + 2 + 1) / 2 * 2) * 2 * sizeof(T);   // RsDirGeo::DEPTH strips per warp
-    const long long cw = (long long)v.MW * v.R;
+    const int slots = 16 * v.R * 4 + K + 2 + (K & 1);      // RsDirGeo::SLOTS
+    v.smem = (size_t)(v.nthr / 32) * 3 * (size_t)slots * 2 * sizeof(T);   // RsDirGeo::DEPTH strips per warp
+    v.NSUB = (slots - K - 2) / (v.MW * v.R);               // sub-items per item: as many as fill a strip
+    if (v.NSUB > 8) v.NSUB = 8;
+    while (v.NSUB > 1 && (long long)v.NSUB * v.MW * v.R + K + 2 > M) --v.NSUB;
+    const long long cw = (long long)v.NSUB * v.MW * v.R;
     v.items = (unsigned)((M + cw - 1) / cw);
     if ((long long)v.items * rows >= (1LL << 31)) return false;
     return true;

@@ -790,6 +790,7 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
     if (D > 1) {
         vec = resample_vec_shape<T>(D, mg->K, eh.N, vshp) && dg->d_coefq;
         dir = vec && g_rs_dir && resample_dir_shape<T>(D, mg->K, eh.N, rows, eh.F, dshp) && dshp.PQ == vshp.PQ;
+        if (dir) { static const int rs_ctas = env_int("NWCWT_RS_CTAS", 0); if (rs_ctas >= 1 && rs_ctas <= 8) dshp.ctas_per_sm = rs_ctas; }
         shp = resample_shape<T>(D, mg->K);
         memset(&R, 0, sizeof(R));
         R.ystride = eh.N;
@@ -808,7 +809,7 @@ static int inverse_rows(nwcwt_plan* pl, nwcwt_plan* ep, int gidx, const cx<T>* X
         R.RS = shp.RS;
         R.dRD = make_fastdiv((uint32_t)(ResampleRun<T>::R * D));
         if (vec) { R.WR = vshp.WR; R.WP = vshp.WP; R.RS = (int)vshp.gbytes; R.dRD = vshp.dRD; R.dGT = make_fastdiv(vshp.items); R.dGT.d = vshp.items; }
-        if (dir) { R.G = dshp.G; R.MW = dshp.MW; R.dG = make_fastdiv((uint32_t)dshp.G); R.dF = make_fastdiv((uint32_t)eh.F); R.dGT = make_fastdiv(dshp.items); R.dGT.d = dshp.items; }
+        if (dir) { R.G = dshp.G; R.MW = dshp.MW; R.NSUB = dshp.NSUB; R.dG = make_fastdiv((uint32_t)dshp.G); R.dF = make_fastdiv((uint32_t)eh.F); R.dGT = make_fastdiv(dshp.items); R.dGT.d = dshp.items; }
         R.coefq = (const T*)dg->d_coefq;
         Q.eq = (const T*)dg->d_eq;
         Q.out_mode = NWCWT_OUT_CWT;

@@ -187,7 +187,7 @@ static int inverse_rows(const HostPlan& hp, const HostPlan& eh_in, const MrGroup
             resample_coefq<T>(mg->coef.data(), D, mg->K, vshp.PQ, coefq.data());
             R.coefq = coefq.data();
             R.WR = vshp.WR; R.WP = vshp.WP; R.RS = (int)vshp.gbytes; R.dRD = vshp.dRD; R.dGT = make_fastdiv(vshp.items); R.dGT.d = vshp.items;
-            if (dir) { R.G = dshp.G; R.MW = dshp.MW; R.dG = make_fastdiv((uint32_t)dshp.G); R.dF = make_fastdiv((uint32_t)eh.F); R.dGT = make_fastdiv(dshp.items); R.dGT.d = dshp.items; }
+            if (dir) { R.G = dshp.G; R.MW = dshp.MW; R.NSUB = dshp.NSUB; R.dG = make_fastdiv((uint32_t)dshp.G); R.dF = make_fastdiv((uint32_t)eh.F); R.dGT = make_fastdiv(dshp.items); R.dGT.d = dshp.items; }
         }
         Q.eq = eq.data();
         Q.out_mode = OUT_CWT;
