@@ -14,7 +14,7 @@ OBJ = os.path.join(HERE, "build" + _SUF)
 LIB = os.path.join(HERE, "libnwcwt%s.so" % _SUF)
 SOURCES = ["nwcwt.cu", "k_short_f32.cu", "k_short_f64.cu", "k_passA_f32.cu", "k_passA_f64.cu",
            "k_passB_f32.cu", "k_passB_f64.cu", "k_long2_f32_c0.cu", "k_long2_f32_c1.cu", "k_long2_f32_c2.cu",
-           "k_long2_f32_c3.cu", "k_long2_f64.cu", "k_short2_f32.cu", "k_short2_f64.cu", "k_resample_f32.cu",
+           "k_long2_f32_c3.cu", "k_long2_f64.cu", "k_short2_f32.cu", "k_short2_f64.cu", "k_short3_f32.cu", "k_resample_f32.cu",
            "k_resample_f64.cu", "k_resample_vec_f32_p4_m2.cu", "k_resample_vec_f32_p4_m1.cu", "k_resample_vec_f32_p2_m2.cu",
            "k_resample_vec_f32_p2_m1.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -6,6 +6,7 @@
 #include "nw_kernels.cuh"
 #include "nw_kernels2.cuh"
 #include "nw_kernels3.cuh"
+#include "nw_kernels4.cuh"
 #include "nw_resample.cuh"
 
 namespace nw {
@@ -34,6 +35,10 @@ cudaError_t launch_short2(int sp, const Short2Params<T>& P, unsigned grid, int n
 // the same kernel with the epoch reduction fused in (nw_kernels3.cuh: short2_epochs_body); kind 0 = mean power, 1 = ITC
 template <typename T>
 cudaError_t launch_short2_epochs(int sp, int kind, const Short2Params<T>& P, unsigned grid, int nthr, size_t smem, cudaStream_t s);
+// fused short-row kernel with resampled rows (nw_kernels4.cuh): abs / power output
+template <typename T> cudaError_t prepare_short3();
+template <typename T>
+cudaError_t launch_short3(const Short3Params<T>& P, unsigned grid, int nthr, size_t smem, cudaStream_t s);
 // interpolation kernel of the resampled rows (nw_resample.cuh); K = taps, mode = OUT_ABS / OUT_POWER
 template <typename T> cudaError_t prepare_resample();
 template <typename T> bool has_resample(int K);

@@ -74,6 +74,9 @@ struct HostPlan {
     int short2 = 0, tpshS = 0, nthrS2 = 256;
     Fft2Plan stS{};
     size_t smem_S2 = 0;
+    // the same with resampled rows (nw_kernels4.cuh; groups hold the per-decimation sub-plans): 0 = not used
+    int short3 = 0, tpshS3 = 0, nthrS3 = 256, yslotsS3 = 0, tpitchS3 = 0;
+    size_t smem_S3 = 0;
     // fast long path (packed in-place engine, nw_kernels2.cuh); 0 = not available for this N
     int fast = 0;
     int N1f = 0, N2f = 0, tpshA = 0, tpshB = 0;
@@ -560,7 +563,8 @@ inline void plan_shape_short2(HostPlan& hp) {
     }
 }
 
-inline void plan_multirate(HostPlan& hp);
+inline void plan_multirate(HostPlan& hp, bool shortrows);
+inline void plan_shape_short3(HostPlan& hp);
 
 inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) {
     const size_t cs = cx_size(hp.dtype);
@@ -587,6 +591,10 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
                     int nt = (int)std::min<long long>(512, std::max<long long>(64, (work + 31) / 32 * 32));
                     hp.nthr_short = nt;
                     plan_shape_short2(hp);
+                    if (hp.short2 && env_int("NWCWT_SHORT3", 0)) {   // band-limited rows at decimated lengths (nw_kernels4.cuh): opt-in, slower than the exact kernel on cfg3 so far (profiles/r02)
+                        plan_multirate(hp, true);
+                        plan_shape_short3(hp);
+                    }
                     return true;
                 }
             }
@@ -627,7 +635,7 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
         hp.generic_ok = 0;
         hp.ring = (int)std::max<long long>(1, std::min<long long>(64, (256LL << 20) / (N * (long long)cs)));
         plan_narrow(hp);
-        plan_multirate(hp);
+        plan_multirate(hp, false);
         return true;
     }
     hp.N1 = (int)best1;
@@ -644,7 +652,7 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
     long long ring = (long long)((48u << 20) / slot);
     hp.ring = (int)std::max<long long>(1, std::min<long long>(ring, 64));
     plan_narrow(hp);
-    plan_multirate(hp);
+    plan_multirate(hp, false);
     return true;
 }
 
@@ -948,9 +956,16 @@ inline MrCost mr_cost(int dtype) {
 // the interpolation kernels a decimation can use: vector kernel (nw_resample.cuh: resample_vec_body) for even D in fp32
 inline bool resample_is_vec(int dtype, int D) { return dtype == 0 && (D & 1) == 0; }
 
-inline void plan_multirate(HostPlan& hp) {
+inline std::shared_ptr<HostPlan> make_sub_plan_short(const HostPlan& hp, const std::vector<int>& fidx, int D,
+                                                     const std::vector<std::pair<long long, long long>>& bands);
+
+// short == false: long rows on the packed two-pass kernels (decimated rows go through the interpolation kernels of
+// nw_resample.cuh).  short == true: rows that fit one CTA (nw_kernels4.cuh): any decimation whose length has a packed plan.
+inline void plan_multirate(HostPlan& hp, bool shortrows) {
     hp.groups.clear();
-    if (hp.path != 1 || !hp.fast || hp.F <= 0 || hp.resample == 0 || hp.Nd > 0) return;
+    if (hp.F <= 0 || hp.resample == 0 || hp.Nd > 0) return;
+    if (!shortrows && (hp.path != 1 || !hp.fast)) return;
+    if (shortrows && (hp.path != 0 || !hp.short2 || hp.dtype != 0 || hp.family == FAM_TABLE)) return;
     if (env_int("NWCWT_NO_RESAMPLE", 0)) return;
     const long long N = hp.N;
     const double tol = hp.resample_tol > 0 ? hp.resample_tol : (hp.dtype == 0 ? 1e-6 : 5e-14);
@@ -961,11 +976,18 @@ inline void plan_multirate(HostPlan& hp) {
     // lengths the host emulation can afford)
     long long MMIN = env_int("NWCWT_RESAMPLE_MMIN", 16384);
     if (MMIN < 64) MMIN = 64;
-    const MrCost cm = mr_cost(hp.dtype);
+    if (shortrows) MMIN = 48;
+    MrCost cm = mr_cost(hp.dtype);
+    if (shortrows) cm = MrCost{3.0, 0.9, 0.04, 0.9, 0.04};   // measured on cfg3 (profiles/r02): exact row 3.9 ps per point
     // candidate decimations: divisors D of N with a fast plan at N / D
     std::vector<int> cands;
     for (int D = 2; D <= 64; ++D) {
         if (N % D || N / D < MMIN) continue;
+        if (shortrows) {
+            Fft2Plan t;
+            if (plan_packed(N / D, t)) cands.push_back(D);
+            continue;
+        }
         HostPlan t;
         t.dtype = hp.dtype; t.N = N / D; t.F = 1;
         plan_shape_fast(t);
@@ -988,7 +1010,7 @@ inline void plan_multirate(HostPlan& hp) {
     // smallest even K (and its best beta) for which every listed row meets the tolerance at decimation D
     auto design = [&](int D, const std::vector<int>& rows, int& K, int& bsel, double& err) -> bool {
         const long long M = N / D;
-        const int kcap = resample_is_vec(hp.dtype, D) ? std::max(kmax_vec, kmin) : kmax;
+        const int kcap = (shortrows || resample_is_vec(hp.dtype, D)) ? std::max(kmax_vec, kmin) : kmax;
         for (int k = kmin; k <= kcap; k += 2) {
             double best = 1e300;
             int bb = 0;
@@ -1017,7 +1039,7 @@ inline void plan_multirate(HostPlan& hp) {
             if (B + 2 > M) continue;
             int K, b; double err;
             if (!design(D, std::vector<int>{i}, K, b, err)) continue;
-            const bool vec = resample_is_vec(hp.dtype, D);
+            const bool vec = shortrows || resample_is_vec(hp.dtype, D);
             const double cost = cm.engine / D + (vec ? cm.fir0 + cm.fir_tap * K : cm.firs0 + cm.firs_tap * K);
             if (cost < best) { best = cost; pickD[(size_t)i] = D; }
         }
@@ -1037,7 +1059,7 @@ inline void plan_multirate(HostPlan& hp) {
         if (g.fidx.empty()) continue;
         std::vector<std::pair<long long, long long>> bands;
         for (int i : g.fidx) bands.push_back(std::make_pair(prof[(size_t)i].rlo, prof[(size_t)i].rhi));
-        g.sub = make_sub_plan(hp, g.fidx, D, bands);
+        g.sub = shortrows ? make_sub_plan_short(hp, g.fidx, D, bands) : make_sub_plan(hp, g.fidx, D, bands);
         bool ok = (bool)g.sub;
         if (ok && D > 1) {
             int bsel = 0;
@@ -1071,6 +1093,73 @@ inline void plan_multirate(HostPlan& hp) {
         hp.groups.push_back(std::move(g));
     }
     if (hp.groups.size() == 1 && hp.groups[0].D == 1) hp.groups.clear();   // nothing resampled after all
+}
+
+// Short rows: the plan of a frequency subset at length M = N / D (D == 1: exact rows): bands (centred on bin 0 for D > 1)
+// and the packed M-point plan.
+inline std::shared_ptr<HostPlan> make_sub_plan_short(const HostPlan& hp, const std::vector<int>& fidx, int D,
+                                                     const std::vector<std::pair<long long, long long>>& bands) {
+    std::shared_ptr<HostPlan> sp = std::make_shared<HostPlan>();
+    HostPlan& s = *sp;
+    s.device = hp.device; s.dtype = hp.dtype; s.family = hp.family; s.interpolate = hp.interpolate;
+    s.N = hp.N / D;
+    s.Nd = hp.N;
+    s.F = (int)fidx.size();
+    s.sfreq = hp.sfreq; s.p0 = hp.p0; s.p1 = hp.p1; s.p2 = hp.p2; s.prune_eps = hp.prune_eps;
+    s.resample = 0;
+    for (int i : fidx) {
+        s.freqs.push_back(hp.freqs[(size_t)i]);
+        if (!hp.aux.empty()) s.aux.push_back(hp.aux[(size_t)i]);
+    }
+    plan_geometry(s);
+    plan_bands(s);
+    if (D > 1) {
+        s.band_bins = 0;
+        for (size_t q = 0; q < s.rec.size(); ++q) {   // the resample band, centred on transform bin 0
+            FreqRec& r = s.rec[q];
+            r.lo = (int)std::max<long long>(r.lo, bands[q].first);
+            r.hi = (int)std::max<long long>(r.lo, std::min<long long>(r.hi, bands[q].second));
+            s.band_bins += r.hi - r.lo;
+            const int kc = r.lo + (r.hi - r.lo) / 2;
+            r.shift = kc;
+            r.lo -= kc;
+            r.hi -= kc;
+        }
+    }
+    s.path = 0;
+    if (!plan_packed(s.N, s.stS)) return nullptr;
+    return sp;
+}
+
+// Shape of the resampled short-row kernel (nw_kernels4.cuh) once the groups exist: NF = 2 frequencies per unit when the
+// tiles leave two CTAs per SM, else one.
+inline void plan_shape_short3(HostPlan& hp) {
+    hp.short3 = 0;
+    if (hp.groups.empty()) return;
+    long long mmax = 0, tp = 0;
+    for (const MrGroup& g : hp.groups) {
+        if (!g.sub) { hp.groups.clear(); return; }
+        if (g.D > 1 && (g.K & 1 || g.K < 4 || g.K > 12)) { hp.groups.clear(); return; }
+        for (int t : g.t0) if (t != 1 - g.K / 2) { hp.groups.clear(); return; }
+        const long long M = g.sub->N;
+        mmax = std::max(mmax, M);
+        tp = std::max(tp, g.D == 1 ? hp.N : M * (long long)(g.D | 1));
+    }
+    const size_t c2 = 2 * cx_size(hp.dtype), p2 = cx_size(hp.dtype);
+    int pick = -1;
+    const int forced = env_int("NWCWT_TPSH_S3", -1);
+    for (int t = 1; t >= 0 && pick < 0; --t) {
+        if (forced >= 0 && t != forced) continue;
+        const size_t ys = (size_t)std::max<long long>(hp.N, mmax << t);
+        const size_t bytes = ((size_t)hp.N + ys) * c2 + ((size_t)tp << t) * p2 + 1280;
+        if (bytes <= (t ? SMEM_HALF : SMEM_MAX)) { pick = t; hp.yslotsS3 = (int)ys; hp.smem_S3 = bytes; }
+    }
+    if (pick < 0) { hp.groups.clear(); return; }
+    hp.short3 = 1;
+    hp.tpshS3 = pick;
+    hp.tpitchS3 = (int)tp;
+    int v = (env_int("NWCWT_NTHR_S3", 256) + 31) / 32 * 32;
+    hp.nthrS3 = v < 64 ? 64 : v > 512 ? 512 : v;
 }
 
 }  // namespace nw

@@ -221,6 +221,10 @@ struct nwcwt_plan {
     void* d_rec = nullptr;
     void* d_table = nullptr;
     void* d_wtab = nullptr;                         // weight table of the bands (nw_plan.h: build_weight_table)
+    // resampled short rows (nw_kernels4.cuh): the device array of Short3Group and everything it points to
+    void* d_s3groups = nullptr;
+    int s3_units = 0;
+    std::vector<void*> s3_allocs;
     const std::vector<double>* eq_host = nullptr;   // sub-plan of a resampled group: the group's equaliser, folded into d_wtab
     // host-call resources
     void* h_in_dev[2] = {nullptr, nullptr};
@@ -355,6 +359,7 @@ static int upload_tw(void** dptr, long long count, long long P, long long step) 
 }
 
 template <typename T> static int ensure_device_t(nwcwt_plan* pl);
+template <typename T> static int ensure_device_short3(nwcwt_plan* pl);
 template <typename T>
 static int run_transform(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
                          int bl, long long blo, long long bhi, void* ws, size_t ws_bytes, cudaStream_t stream,
@@ -421,6 +426,59 @@ static int ensure_device_bluestein(nwcwt_plan* pl) {
     return 0;
 }
 
+// Resampled short rows: per group the M-point twiddles, the centred bands with their weight table (1 / N and the
+// group's equaliser folded in), the interpolation weights and the frequency map; then the array of Short3Group itself.
+template <typename T>
+static int ensure_device_short3(nwcwt_plan* pl) {
+    HostPlan& hp = pl->hp;
+    std::vector<Short3Group<T>> gs;
+    int unit = 0;
+    auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+        CUDA_TRY(cudaMalloc(dst, bytes ? bytes : 16));
+        pl->s3_allocs.push_back(*dst);
+        if (bytes) CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    int rc;
+    for (const MrGroup& mg : hp.groups) {
+        HostPlan sub = *mg.sub;   // build_weight_table sets FreqRec::woff
+        std::vector<T> wtab;
+        if (!build_weight_table<T>(sub, mg.D > 1 ? mg.eq.data() : nullptr, (size_t)256 << 20, wtab))
+            return fail(NWCWT_ERR_UNSUPPORTED, "short rows: weight table too large");
+        Short3Group<T> g;
+        memset(&g, 0, sizeof(g));
+        g.M = (int)sub.N; g.D = mg.D; g.K = mg.D > 1 ? mg.K : 0; g.F = sub.F;
+        g.DP = mg.D > 1 ? (mg.D | 1) : 1;
+        g.PCH = (mg.D + 3) / 4;
+        g.unit0 = unit;
+        g.nunits = (sub.F + (1 << hp.tpshS3) - 1) >> hp.tpshS3;
+        unit += g.nunits;
+        g.st = sub.stS;
+        g.dD = make_fastdiv((uint32_t)mg.D);
+        g.dM = make_fastdiv((uint32_t)g.M);
+        g.dPer = make_fastdiv((uint32_t)(g.M * g.PCH));
+        std::vector<cx<T>> tw;
+        fill_twiddles<T>(tw, sub.N, sub.N, 1);
+        void* d = nullptr;
+        if ((rc = up(tw.data(), tw.size() * sizeof(cx<T>), &d))) return rc;
+        g.tw = (const cx<T>*)d;
+        if ((rc = up(sub.rec.data(), sub.rec.size() * sizeof(FreqRec), &d))) return rc;
+        g.rec = (const FreqRec*)d;
+        if ((rc = up(wtab.data(), wtab.size() * sizeof(T), &d))) return rc;
+        g.wtab = (const T*)d;
+        std::vector<T> coef(mg.coef.begin(), mg.coef.end());
+        if ((rc = up(coef.data(), coef.size() * sizeof(T), &d))) return rc;
+        g.coef = (const T*)d;
+        if ((rc = up(mg.fidx.data(), mg.fidx.size() * sizeof(int), &d))) return rc;
+        g.fmap = (const int*)d;
+        gs.push_back(g);
+    }
+    CUDA_TRY(cudaMalloc(&pl->d_s3groups, gs.size() * sizeof(Short3Group<T>)));
+    CUDA_TRY(cudaMemcpy(pl->d_s3groups, gs.data(), gs.size() * sizeof(Short3Group<T>), cudaMemcpyHostToDevice));
+    pl->s3_units = unit;
+    return 0;
+}
+
 template <typename T>
 static int ensure_device_t(nwcwt_plan* pl) {
     HostPlan& hp = pl->hp;
@@ -472,6 +530,10 @@ static int ensure_device_t(nwcwt_plan* pl) {
     if (hp.path == 0) {
         CUDA_TRY(prepare_short<T>());
         if (hp.short2) CUDA_TRY(prepare_short2<T>());
+        if (hp.short3) {
+            if ((rc = ensure_device_short3<T>(pl))) return rc;
+            CUDA_TRY(prepare_short3<T>());
+        }
     } else {
         CUDA_TRY(prepare_passA<T>());
         CUDA_TRY(prepare_passB<T>());
@@ -638,10 +700,48 @@ static int launch_short2_epochs_t(nwcwt_plan* pl, const void* signals, void* out
     return 0;
 }
 
+// resampled short rows: one CTA per signal pair (and share of the work units)
+template <typename T>
+static int launch_short3_t(nwcwt_plan* pl, const void* signals, void* out, long long S, int output, int bl, long long blo,
+                           long long bhi, cudaStream_t stream) {
+    const HostPlan& hp = pl->hp;
+    Short3Params<T> P;
+    memset(&P, 0, sizeof(P));
+    P.signals = (const T*)signals;
+    P.out = out;
+    P.N = (int)hp.N;
+    P.F_out = hp.F;
+    P.S = (int)S;
+    P.tpsh = hp.tpshS3;
+    P.out_mode = output;
+    P.bl_mode = bl;
+    P.bl_lo = (int)blo;
+    P.bl_hi = (int)bhi;
+    P.st = hp.stS;
+    P.tw = (const cx<T>*)pl->d_tw;
+    P.groups = (const Short3Group<T>*)pl->d_s3groups;
+    P.ngroups = (int)hp.groups.size();
+    P.nunits = pl->s3_units;
+    P.yslots = hp.yslotsS3;
+    P.tpitch = hp.tpitchS3;
+    const long long npairs = (S + 1) / 2;
+    const long long target = 6LL * device_sms(hp.device);
+    long long fs = (target + npairs - 1) / npairs;
+    if (fs > P.nunits) fs = P.nunits;
+    if (fs < 1) fs = 1;
+    P.fsplit = (int)fs;
+    const long long grid = npairs * fs;
+    if (grid > 2147483647LL) return fail(NWCWT_ERR_INVALID, "too many signals for one launch");
+    { LaunchScope ls(0, stream); CUDA_TRY(launch_short3<T>(P, (unsigned)grid, hp.nthrS3, hp.smem_S3, stream)); }
+    return 0;
+}
+
 template <typename T>
 static int launch_short(nwcwt_plan* pl, const void* signals, void* out, void* spectra, long long S, int output,
                         int bl, long long blo, long long bhi, cudaStream_t stream, bool forward_only) {
     const HostPlan& hp = pl->hp;
+    if (hp.short3 && !forward_only && !g_force_generic && !g_exact && output != NWCWT_OUT_CWT)
+        return launch_short3_t<T>(pl, signals, out, S, output, bl, blo, bhi, stream);
     if (hp.short2 && !forward_only && !g_force_generic)
         return launch_short2<T>(pl, signals, out, S, output, bl, blo, bhi, stream);
     ShortParams<T> P;
@@ -1187,6 +1287,7 @@ int nwcwt_plan_create(nwcwt_plan** out, const nwcwt_plan_desc* d) {
         }
     }
     for (const MrGroup& mg : hp.groups) {
+        if (hp.short3) break;   // short rows: the groups live inside one kernel (ensure_device_short3)
         nwcwt_plan::Group g;
         g.sub = new nwcwt_plan();
         g.sub->hp = *mg.sub;
@@ -1213,6 +1314,9 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
     pl->blu_f = pl->blu_i = nullptr;
     if (pl->on_device || pl->h_stream[0]) {
         cudaSetDevice(pl->hp.device);
+        for (void* q : pl->s3_allocs) if (q) cudaFree(q);
+        pl->s3_allocs.clear();
+        if (pl->d_s3groups) cudaFree(pl->d_s3groups);
         void* ptrs[] = {pl->d_tw, pl->d_twA, pl->d_twB, pl->d_twH, pl->d_twL, pl->d_rec, pl->d_table, pl->d_wtab, pl->d_ditpos, pl->d_chirp, pl->d_twA2, pl->d_twB2,
                         pl->h_in_dev[0], pl->h_in_dev[1], pl->h_out_dev[0], pl->h_out_dev[1], pl->h_ws[0], pl->h_ws[1]};
         for (void* p : ptrs)
@@ -1243,7 +1347,7 @@ int nwcwt_plan_get_info(const nwcwt_plan* pl, nwcwt_plan_info* info) {
         info->group_D[g] = mg.D;
         info->group_K[g] = mg.K;
         info->group_rows[g] = (int32_t)mg.fidx.size();
-        info->group_n1[g] = mg.sub->N1f;
+        info->group_n1[g] = hp.short3 ? (int32_t)mg.sub->N : mg.sub->N1f;
         info->group_n2[g] = mg.sub->N2f;
         info->group_err[g] = mg.err;
     }

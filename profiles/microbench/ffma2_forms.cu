@@ -46,8 +46,10 @@ int main() {
     float2* in; float* out;
     cudaMalloc(&in, 1 << 20); cudaMemset(in, 0, 1 << 20); cudaMalloc(&out, 4096);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int iters = 2000, grid = 148 * 4;
-    for (int mode = 0; mode < 3; ++mode) {
+    const int iters = 2000;
+    for (int wps = 1; wps <= 4; wps *= 2)   // resident warps per scheduler (128-thread CTAs, 128 registers: at most 4)
+    for (int mode = 0; mode < 2; ++mode) {
+        const int grid = 148 * wps;
         float best = 1e9;
         for (int r = 0; r < 4; ++r) {
             cudaEventRecord(e0);
@@ -58,7 +60,7 @@ int main() {
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (r && ms < best) best = ms;
         }
         const double n = (double)grid * 128 * iters * R * (4.0 * K + 4);
-        printf("mode %d: %.3f ms, %.2f T packed thread-instr/s (plain-chain peak 18.25)\n", mode, best, n / best / 1e9);
+        printf("warps/scheduler %d mode %d: %.3f ms, %.2f T packed thread-instr/s (plain-chain peak 18.25)\n", wps, mode, best, n / best / 1e9);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;

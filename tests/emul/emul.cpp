@@ -17,6 +17,7 @@
 #include "../../ninwavelets_b200/csrc/nw_kernels2.cuh"
 #include "../../ninwavelets_b200/csrc/nw_kernels3.cuh"
 #include "../../ninwavelets_b200/csrc/nw_resample.cuh"
+#include "../../ninwavelets_b200/csrc/nw_kernels4.cuh"
 #include "../../ninwavelets_b200/csrc/nw_plan.h"
 
 #include <ucontext.h>
@@ -272,6 +273,49 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
     make_table<T>(hp, table);
     SpecParams<T> sp = make_sp<T>(hp, table);
     const size_t esz = output == OUT_CWT ? sizeof(cx<T>) : sizeof(T);
+    if (hp.path == 0 && hp.short3 && output != OUT_CWT && !(g_mode & 2) && !(g_mode & 128)) {
+        // resampled short rows (nw_kernels4.cuh): mirrors nwcwt.cu: ensure_device_short3 / launch_short3_t
+        std::vector<cx<T>> tw;
+        fill_tw<T>(tw, hp.N, hp.N, 1);
+        const size_t ng = hp.groups.size();
+        std::vector<Short3Group<T>> gs(ng);
+        std::vector<HostPlan> subs(ng);
+        std::vector<std::vector<T>> wtabs(ng), coefs(ng);
+        std::vector<std::vector<cx<T>>> tws(ng);
+        int unit = 0;
+        for (size_t gi = 0; gi < ng; ++gi) {
+            const MrGroup& mg = hp.groups[gi];
+            subs[gi] = *mg.sub;
+            if (!build_weight_table<T>(subs[gi], mg.D > 1 ? mg.eq.data() : nullptr, (size_t)256 << 20, wtabs[gi])) return -2;
+            Short3Group<T>& g = gs[gi];
+            memset(&g, 0, sizeof(g));
+            g.M = (int)subs[gi].N; g.D = mg.D; g.K = mg.D > 1 ? mg.K : 0; g.F = subs[gi].F;
+            g.DP = mg.D > 1 ? (mg.D | 1) : 1; g.PCH = (mg.D + 3) / 4;
+            g.unit0 = unit; g.nunits = (g.F + (1 << hp.tpshS3) - 1) >> hp.tpshS3; unit += g.nunits;
+            g.st = subs[gi].stS;
+            g.dD = make_fastdiv((uint32_t)mg.D); g.dM = make_fastdiv((uint32_t)g.M); g.dPer = make_fastdiv((uint32_t)(g.M * g.PCH));
+            fill_tw<T>(tws[gi], g.M, g.M, 1);
+            coefs[gi].assign(mg.coef.begin(), mg.coef.end());
+            g.tw = tws[gi].data(); g.rec = subs[gi].rec.data(); g.wtab = wtabs[gi].data(); g.coef = coefs[gi].data();
+            g.fmap = mg.fidx.data();
+        }
+        Short3Params<T> P;
+        memset(&P, 0, sizeof(P));
+        P.signals = (const T*)signals; P.out = out; P.N = (int)hp.N; P.F_out = hp.F; P.S = (int)S; P.tpsh = hp.tpshS3;
+        P.out_mode = output; P.bl_mode = bl; P.bl_lo = (int)blo; P.bl_hi = (int)bhi; P.st = hp.stS; P.tw = tw.data();
+        P.groups = gs.data(); P.ngroups = (int)ng; P.nunits = unit; P.yslots = hp.yslotsS3; P.tpitch = hp.tpitchS3;
+        P.fsplit = unit < 3 ? unit : 3;
+        std::vector<char> sm(hp.smem_S3 + 64);
+        char* smp = (char*)(((uintptr_t)sm.data() + 31) & ~(uintptr_t)31);
+        const int nt = (g_mode & 4) ? 1 : hp.nthrS3;
+        const long long nblk = ((S + 1) / 2) * P.fsplit;
+        for (long long b = 0; b < nblk; ++b)
+            Fibers::get().run(nt, [&](int t) {
+                if (output == OUT_POWER) short3_body<T, OUT_POWER>(P, smp, (int)b, t, nt);
+                else short3_body<T, OUT_ABS>(P, smp, (int)b, t, nt);
+            });
+        return 0;
+    }
     if (hp.path == 0 && hp.short2 && !(g_mode & 2)) {
         std::vector<cx<T>> tw;
         fill_tw<T>(tw, hp.N, hp.N, 1);

@@ -213,3 +213,57 @@ def test_emul_resampled_rows_at_cfg2_length():
     p = emul_transform(desc_from_oracle_family(fam, freqs, n, dtype=0), x, output=2)
     e = l2_rel_err(p[0], ref)
     assert e.max() <= F32_TOL, e
+
+
+@pytest.mark.parametrize("kind,kw,n,freqs,bl", [
+    ("morlet", dict(sigma=7.0), 1500, np.array([1., 3., 8., 13., 21., 34., 55., 89., 100.]), ("zscore", 0.0, 0.2)),
+    ("morse", {}, 1500, np.array([2., 5., 17., 60., 99.]), None),
+    ("morse", {}, 300, np.array([1., 7., 30., 80.]), None),
+    ("shannon", {}, 1200, np.array([3., 10., 40., 90.]), None),
+    ("morse", dict(interpolate=True), 1000, np.array([4., 25., 70.]), ("ratio", 0.1, 0.4)),
+])
+def test_emul_resampled_short_rows(kind, kw, n, freqs, bl, monkeypatch):
+    """Resampled SHORT rows (nw_kernels4.cuh; nw_plan.h: plan_multirate(short)): rows that fit one CTA are transformed at
+    N / D points and interpolated inside the fused kernel.  fp32 power and abs (with a Baseline epilogue where given)
+    against the oracle, every row relative to itself, and against the same plan forced to exact transforms (flag 128:
+    nw_kernels3.cuh); three signals (an odd count: the last CTA owns one signal).  The path is opt-in (NWCWT_SHORT3)."""
+    monkeypatch.setenv("NWCWT_SHORT3", "1")
+    rng = np.random.default_rng(23)
+    fam = orc.Family(kind, sfreq=1000.0, **kw)
+    x32 = rng.standard_normal((3, n)).astype(np.float32)
+    d32 = desc_from_oracle_family(fam, freqs, n, dtype=0)
+    modes = {"mean": 1, "ratio": 2, "percent": 3, "log": 4, "zscore": 5, "zlog": 6}
+    args = {}
+    if bl is not None:
+        lo, hi = int(bl[1] * 1000), int(bl[2] * 1000)
+        args = dict(baseline=modes[bl[0]], lo=lo, hi=hi)
+    ref = np.stack([orc.power(fam, xi.astype(np.float64), freqs) for xi in x32])
+    refb = ref if bl is None else np.stack([orc.baseline_rows(r, 1000.0, bl[1], bl[2], bl[0]) for r in ref])
+    p = emul_transform(d32, x32, output=2, **args)
+    e = l2_rel_err(p.reshape(-1, n), refb.reshape(-1, n))
+    assert e.max() <= F32_TOL, (kind, e)
+    pe = emul_transform(d32, x32, output=2, force_long=128, **args)          # exact transforms (short2 kernel), same plan
+    assert l2_rel_err(p.reshape(-1, n), pe.astype(np.float64).reshape(-1, n)).max() <= F32_TOL, kind
+    a = emul_transform(d32, x32, output=1)
+    assert l2_rel_err(a.reshape(-1, n), np.sqrt(ref).reshape(-1, n)).max() <= F32_TOL, kind
+
+
+def test_emul_short_resampling_is_planned(monkeypatch):
+    """Planner facts (host only): config 3's plan (Morlet, N = 1500, 1..100 Hz, fp32) resamples, its groups cover every
+    frequency once with decimated lengths that divide N, the bound of every group is below the default tolerance; fp64 and
+    `resample=False` keep the exact short-row kernel, and so does the default (the path is opt-in: NWCWT_SHORT3)."""
+    from ninwavelets_b200 import _backend as be
+    fr = np.arange(1, 101.0)
+    fam = orc.Family("morlet", sfreq=1000.0, sigma=7.0)
+    aux = np.array([orc.peak_freq(fam, f) for f in fr])
+    kw = dict(device=0, family=be.MORLET, interpolate=False, n=1500, sfreq=1000.0, freqs=fr, p0=fam.sigma,
+              p1=fam.c * np.float_power(np.pi, -1 / 4), p2=fam.k, aux=aux)
+    assert be.Plan(dtype=np.float32, **kw).info()["groups"] == []
+    monkeypatch.setenv("NWCWT_SHORT3", "1")
+    g = be.Plan(dtype=np.float32, **kw).info()["groups"]
+    assert g and sum(x["rows"] for x in g) == 100
+    assert all(1500 % x["D"] == 0 and x["n1"] * x["D"] == 1500 for x in g)
+    assert all(x["D"] == 1 or (0 < x["err"] <= 1e-6 and x["K"] % 2 == 0 and 4 <= x["K"] <= 12) for x in g)
+    assert sum(x["rows"] * 1500 // x["D"] for x in g) < 0.4 * 100 * 1500
+    assert be.Plan(dtype=np.float64, **kw).info()["groups"] == []
+    assert be.Plan(dtype=np.float32, resample=False, **kw).info()["groups"] == []

@@ -504,3 +504,35 @@ def test_too_long_raises(nw):
     with pytest.raises(be.BackendError):
         be.Plan(device=0, dtype=np.float32, family=be.MORSE, interpolate=False, n=(1 << 31) + 7, sfreq=1000.0,
                 freqs=[1.0, 2.0], p0=17.5, p1=3.0)
+
+
+@pytest.mark.parametrize("mode", [None, "zscore", "mean", "ratio", "percent", "log", "zlog"])
+def test_resampled_short_rows_cfg3_slice(nw, mode, monkeypatch):
+    """Resampled SHORT rows (nw_kernels4.cuh) at BASELINE.json config-3 row size: Morlet(7) power at 1..100 Hz on an odd
+    number of 1500-sample epochs, fp32, plain and with every Baseline mode as the kernel's epilogue, against the oracle
+    (every row relative to itself) and against the exact short-row kernel (`resample=False`); abs output as well.
+    The path is opt-in (NWCWT_SHORT3=1, read when the plan is created)."""
+    monkeypatch.setenv("NWCWT_SHORT3", "1")
+    n = 1500
+    fam = orc.Family("morlet", sfreq=1000, sigma=7.)
+    fr = np.arange(1, 101.0)
+    x32 = orc.meg_epochs_like(7, n).astype(np.float32)
+    m = make(nw, "morlet", dict(sfreq=1000, sigma=7.), dtype="float32")
+    bl = None if mode is None else (mode, 0.0, 0.2)
+    p = m.power(x32, fr, baseline=bl)
+    groups = m._plan.info()["groups"]
+    assert groups and sum(g["rows"] for g in groups) == 100 and any(g["D"] > 1 for g in groups), groups
+    ref = np.stack([orc.power(fam, xi.astype(np.float64), fr) for xi in x32])
+    refb = ref if mode is None else np.stack([orc.baseline_rows(r, 1000., 0.0, 0.2, mode) for r in ref])
+    e = l2_rel_err(p.reshape(-1, n).astype(np.float64), refb.reshape(-1, n))
+    assert e.max() <= F32_TOL, (mode, e.max())
+    exact = make(nw, "morlet", dict(sfreq=1000, sigma=7.), dtype="float32", resample=False)
+    pe = exact.power(x32, fr, baseline=bl)
+    assert exact._plan.info()["groups"] == []
+    d = l2_rel_err(p.reshape(-1, n).astype(np.float64), pe.reshape(-1, n).astype(np.float64)).max()
+    assert d <= F32_TOL, (mode, d)
+    if mode is None:
+        a = m.abs(x32, None)
+        assert l2_rel_err(a.reshape(-1, n).astype(np.float64), np.sqrt(ref).reshape(-1, n)).max() <= F32_TOL
+    print("short resampled rows, baseline %s: worst row %.3e, vs exact kernel %.3e, groups %s" % (
+        mode, e.max(), d, [(g["D"], g["K"], g["rows"]) for g in groups]))
