@@ -591,7 +591,7 @@ inline bool plan_shape(HostPlan& hp, std::string& err, bool force_long = false) 
                     int nt = (int)std::min<long long>(512, std::max<long long>(64, (work + 31) / 32 * 32));
                     hp.nthr_short = nt;
                     plan_shape_short2(hp);
-                    if (hp.short2 && env_int("NWCWT_SHORT3", 0)) {   // band-limited rows at decimated lengths (nw_kernels4.cuh): opt-in, slower than the exact kernel on cfg3 so far (profiles/r02)
+                    if (hp.short2 && env_int("NWCWT_SHORT3", 1)) {   // band-limited rows at decimated lengths (nw_kernels4.cuh); NWCWT_SHORT3=0: exact kernel only
                         plan_multirate(hp, true);
                         plan_shape_short3(hp);
                     }
@@ -985,7 +985,8 @@ inline void plan_multirate(HostPlan& hp, bool shortrows) {
         if (N % D || N / D < MMIN) continue;
         if (shortrows) {
             Fft2Plan t;
-            if (plan_packed(N / D, t)) cands.push_back(D);
+            const int pq = (D % 4 == 0 && N % 4 == 0) ? 4 : (D % 2 == 0 && N % 2 == 0) ? 2 : 1;
+            if (D / pq <= 32 && plan_packed(N / D, t)) cands.push_back(D);
             continue;
         }
         HostPlan t;
@@ -1131,33 +1132,21 @@ inline std::shared_ptr<HostPlan> make_sub_plan_short(const HostPlan& hp, const s
     return sp;
 }
 
-// Shape of the resampled short-row kernel (nw_kernels4.cuh) once the groups exist: NF = 2 frequencies per unit when the
-// tiles leave two CTAs per SM, else one.
+// Shape of the resampled short-row kernel (nw_kernels4.cuh) once the groups exist.
 inline void plan_shape_short3(HostPlan& hp) {
     hp.short3 = 0;
     if (hp.groups.empty()) return;
-    long long mmax = 0, tp = 0;
     for (const MrGroup& g : hp.groups) {
         if (!g.sub) { hp.groups.clear(); return; }
         if (g.D > 1 && (g.K & 1 || g.K < 4 || g.K > 12)) { hp.groups.clear(); return; }
         for (int t : g.t0) if (t != 1 - g.K / 2) { hp.groups.clear(); return; }
-        const long long M = g.sub->N;
-        mmax = std::max(mmax, M);
-        tp = std::max(tp, g.D == 1 ? hp.N : M * (long long)(g.D | 1));
+        const int pq = (g.D % 4 == 0 && hp.N % 4 == 0) ? 4 : (g.D % 2 == 0 && hp.N % 2 == 0) ? 2 : 1;
+        if (g.D > 1 && g.D / pq > 32) { hp.groups.clear(); return; }   // lanes per output sample m
     }
-    const size_t c2 = 2 * cx_size(hp.dtype), p2 = cx_size(hp.dtype);
-    int pick = -1;
-    const int forced = env_int("NWCWT_TPSH_S3", -1);
-    for (int t = 1; t >= 0 && pick < 0; --t) {
-        if (forced >= 0 && t != forced) continue;
-        const size_t ys = (size_t)std::max<long long>(hp.N, mmax << t);
-        const size_t bytes = ((size_t)hp.N + ys) * c2 + ((size_t)tp << t) * p2 + 1280;
-        if (bytes <= (t ? SMEM_HALF : SMEM_MAX)) { pick = t; hp.yslotsS3 = (int)ys; hp.smem_S3 = bytes; }
-    }
-    if (pick < 0) { hp.groups.clear(); return; }
+    const size_t bytes = 2 * (size_t)hp.N * 2 * cx_size(hp.dtype) + 512 + 64 * 12 * (cx_size(hp.dtype) / 2);   // short3_smem_bytes
+    if (bytes > SMEM_MAX) { hp.groups.clear(); return; }
     hp.short3 = 1;
-    hp.tpshS3 = pick;
-    hp.tpitchS3 = (int)tp;
+    hp.smem_S3 = bytes;
     int v = (env_int("NWCWT_NTHR_S3", 256) + 31) / 32 * 32;
     hp.nthrS3 = v < 64 ? 64 : v > 512 ? 512 : v;
 }

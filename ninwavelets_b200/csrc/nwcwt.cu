@@ -446,17 +446,11 @@ static int ensure_device_short3(nwcwt_plan* pl) {
         if (!build_weight_table<T>(sub, mg.D > 1 ? mg.eq.data() : nullptr, (size_t)256 << 20, wtab))
             return fail(NWCWT_ERR_UNSUPPORTED, "short rows: weight table too large");
         Short3Group<T> g;
-        memset(&g, 0, sizeof(g));
-        g.M = (int)sub.N; g.D = mg.D; g.K = mg.D > 1 ? mg.K : 0; g.F = sub.F;
-        g.DP = mg.D > 1 ? (mg.D | 1) : 1;
-        g.PCH = (mg.D + 3) / 4;
+        if (!short3_fill_group<T>(g, hp.N, sub.N, mg.D, mg.K, sub.F))
+            return fail(NWCWT_ERR_UNSUPPORTED, "short rows: decimation without a kernel shape");
         g.unit0 = unit;
-        g.nunits = (sub.F + (1 << hp.tpshS3) - 1) >> hp.tpshS3;
         unit += g.nunits;
         g.st = sub.stS;
-        g.dD = make_fastdiv((uint32_t)mg.D);
-        g.dM = make_fastdiv((uint32_t)g.M);
-        g.dPer = make_fastdiv((uint32_t)(g.M * g.PCH));
         std::vector<cx<T>> tw;
         fill_twiddles<T>(tw, sub.N, sub.N, 1);
         void* d = nullptr;
@@ -466,11 +460,16 @@ static int ensure_device_short3(nwcwt_plan* pl) {
         g.rec = (const FreqRec*)d;
         if ((rc = up(wtab.data(), wtab.size() * sizeof(T), &d))) return rc;
         g.wtab = (const T*)d;
-        std::vector<T> coef(mg.coef.begin(), mg.coef.end());
-        if ((rc = up(coef.data(), coef.size() * sizeof(T), &d))) return rc;
-        g.coef = (const T*)d;
+        std::vector<T> coefq(mg.coef.size() + 4);
+        if (mg.D > 1) resample_coefq<T>(mg.coef.data(), mg.D, mg.K, g.PQ, coefq.data());
+        if ((rc = up(coefq.data(), coefq.size() * sizeof(T), &d))) return rc;
+        g.coefq = (const T*)d;
         if ((rc = up(mg.fidx.data(), mg.fidx.size() * sizeof(int), &d))) return rc;
         g.fmap = (const int*)d;
+        std::vector<int> pos((size_t)sub.N);
+        for (int k = 0; k < (int)sub.N; ++k) pos[(size_t)k] = fft2_dit_pos(sub.stS, k);
+        if ((rc = up(pos.data(), pos.size() * sizeof(int), &d))) return rc;
+        g.ditpos = (const int*)d;
         gs.push_back(g);
     }
     CUDA_TRY(cudaMalloc(&pl->d_s3groups, gs.size() * sizeof(Short3Group<T>)));
@@ -712,7 +711,6 @@ static int launch_short3_t(nwcwt_plan* pl, const void* signals, void* out, long 
     P.N = (int)hp.N;
     P.F_out = hp.F;
     P.S = (int)S;
-    P.tpsh = hp.tpshS3;
     P.out_mode = output;
     P.bl_mode = bl;
     P.bl_lo = (int)blo;
@@ -722,8 +720,6 @@ static int launch_short3_t(nwcwt_plan* pl, const void* signals, void* out, long 
     P.groups = (const Short3Group<T>*)pl->d_s3groups;
     P.ngroups = (int)hp.groups.size();
     P.nunits = pl->s3_units;
-    P.yslots = hp.yslotsS3;
-    P.tpitch = hp.tpitchS3;
     const long long npairs = (S + 1) / 2;
     const long long target = 6LL * device_sms(hp.device);
     long long fs = (target + npairs - 1) / npairs;

@@ -282,28 +282,30 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
         std::vector<HostPlan> subs(ng);
         std::vector<std::vector<T>> wtabs(ng), coefs(ng);
         std::vector<std::vector<cx<T>>> tws(ng);
+        std::vector<std::vector<int>> poss(ng);
         int unit = 0;
         for (size_t gi = 0; gi < ng; ++gi) {
             const MrGroup& mg = hp.groups[gi];
             subs[gi] = *mg.sub;
             if (!build_weight_table<T>(subs[gi], mg.D > 1 ? mg.eq.data() : nullptr, (size_t)256 << 20, wtabs[gi])) return -2;
             Short3Group<T>& g = gs[gi];
-            memset(&g, 0, sizeof(g));
-            g.M = (int)subs[gi].N; g.D = mg.D; g.K = mg.D > 1 ? mg.K : 0; g.F = subs[gi].F;
-            g.DP = mg.D > 1 ? (mg.D | 1) : 1; g.PCH = (mg.D + 3) / 4;
-            g.unit0 = unit; g.nunits = (g.F + (1 << hp.tpshS3) - 1) >> hp.tpshS3; unit += g.nunits;
+            if (!short3_fill_group<T>(g, hp.N, subs[gi].N, mg.D, mg.K, subs[gi].F)) return -2;
+            g.unit0 = unit; unit += g.nunits;
             g.st = subs[gi].stS;
-            g.dD = make_fastdiv((uint32_t)mg.D); g.dM = make_fastdiv((uint32_t)g.M); g.dPer = make_fastdiv((uint32_t)(g.M * g.PCH));
             fill_tw<T>(tws[gi], g.M, g.M, 1);
-            coefs[gi].assign(mg.coef.begin(), mg.coef.end());
-            g.tw = tws[gi].data(); g.rec = subs[gi].rec.data(); g.wtab = wtabs[gi].data(); g.coef = coefs[gi].data();
+            coefs[gi].assign(mg.coef.size() + 4, (T)0);
+            if (mg.D > 1) resample_coefq<T>(mg.coef.data(), mg.D, mg.K, g.PQ, coefs[gi].data());
+            g.tw = tws[gi].data(); g.rec = subs[gi].rec.data(); g.wtab = wtabs[gi].data(); g.coefq = coefs[gi].data();
             g.fmap = mg.fidx.data();
+            poss[gi].resize((size_t)g.M);
+            for (int k = 0; k < g.M; ++k) poss[gi][(size_t)k] = fft2_dit_pos(g.st, k);
+            g.ditpos = poss[gi].data();
         }
         Short3Params<T> P;
         memset(&P, 0, sizeof(P));
-        P.signals = (const T*)signals; P.out = out; P.N = (int)hp.N; P.F_out = hp.F; P.S = (int)S; P.tpsh = hp.tpshS3;
+        P.signals = (const T*)signals; P.out = out; P.N = (int)hp.N; P.F_out = hp.F; P.S = (int)S;
         P.out_mode = output; P.bl_mode = bl; P.bl_lo = (int)blo; P.bl_hi = (int)bhi; P.st = hp.stS; P.tw = tw.data();
-        P.groups = gs.data(); P.ngroups = (int)ng; P.nunits = unit; P.yslots = hp.yslotsS3; P.tpitch = hp.tpitchS3;
+        P.groups = gs.data(); P.ngroups = (int)ng; P.nunits = unit;
         P.fsplit = unit < 3 ? unit : 3;
         std::vector<char> sm(hp.smem_S3 + 64);
         char* smp = (char*)(((uintptr_t)sm.data() + 31) & ~(uintptr_t)31);
@@ -311,8 +313,7 @@ static int run(const HostPlan& hp, const void* signals, void* out, long long S, 
         const long long nblk = ((S + 1) / 2) * P.fsplit;
         for (long long b = 0; b < nblk; ++b)
             Fibers::get().run(nt, [&](int t) {
-                if (output == OUT_POWER) short3_body<T, OUT_POWER>(P, smp, (int)b, t, nt);
-                else short3_body<T, OUT_ABS>(P, smp, (int)b, t, nt);
+                short3_body<T>(P, smp, (int)b, t, nt);
             });
         return 0;
     }

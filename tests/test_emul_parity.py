@@ -226,8 +226,7 @@ def test_emul_resampled_short_rows(kind, kw, n, freqs, bl, monkeypatch):
     """Resampled SHORT rows (nw_kernels4.cuh; nw_plan.h: plan_multirate(short)): rows that fit one CTA are transformed at
     N / D points and interpolated inside the fused kernel.  fp32 power and abs (with a Baseline epilogue where given)
     against the oracle, every row relative to itself, and against the same plan forced to exact transforms (flag 128:
-    nw_kernels3.cuh); three signals (an odd count: the last CTA owns one signal).  The path is opt-in (NWCWT_SHORT3)."""
-    monkeypatch.setenv("NWCWT_SHORT3", "1")
+    nw_kernels3.cuh); three signals (an odd count: the last CTA owns one signal)."""
     rng = np.random.default_rng(23)
     fam = orc.Family(kind, sfreq=1000.0, **kw)
     x32 = rng.standard_normal((3, n)).astype(np.float32)
@@ -251,15 +250,16 @@ def test_emul_resampled_short_rows(kind, kw, n, freqs, bl, monkeypatch):
 def test_emul_short_resampling_is_planned(monkeypatch):
     """Planner facts (host only): config 3's plan (Morlet, N = 1500, 1..100 Hz, fp32) resamples, its groups cover every
     frequency once with decimated lengths that divide N, the bound of every group is below the default tolerance; fp64 and
-    `resample=False` keep the exact short-row kernel, and so does the default (the path is opt-in: NWCWT_SHORT3)."""
+    `resample=False` (or NWCWT_SHORT3=0) keep the exact short-row kernel."""
     from ninwavelets_b200 import _backend as be
     fr = np.arange(1, 101.0)
     fam = orc.Family("morlet", sfreq=1000.0, sigma=7.0)
     aux = np.array([orc.peak_freq(fam, f) for f in fr])
     kw = dict(device=0, family=be.MORLET, interpolate=False, n=1500, sfreq=1000.0, freqs=fr, p0=fam.sigma,
               p1=fam.c * np.float_power(np.pi, -1 / 4), p2=fam.k, aux=aux)
+    monkeypatch.setenv("NWCWT_SHORT3", "0")
     assert be.Plan(dtype=np.float32, **kw).info()["groups"] == []
-    monkeypatch.setenv("NWCWT_SHORT3", "1")
+    monkeypatch.delenv("NWCWT_SHORT3")
     g = be.Plan(dtype=np.float32, **kw).info()["groups"]
     assert g and sum(x["rows"] for x in g) == 100
     assert all(1500 % x["D"] == 0 and x["n1"] * x["D"] == 1500 for x in g)

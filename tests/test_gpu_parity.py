@@ -511,8 +511,7 @@ def test_resampled_short_rows_cfg3_slice(nw, mode, monkeypatch):
     """Resampled SHORT rows (nw_kernels4.cuh) at BASELINE.json config-3 row size: Morlet(7) power at 1..100 Hz on an odd
     number of 1500-sample epochs, fp32, plain and with every Baseline mode as the kernel's epilogue, against the oracle
     (every row relative to itself) and against the exact short-row kernel (`resample=False`); abs output as well.
-    The path is opt-in (NWCWT_SHORT3=1, read when the plan is created)."""
-    monkeypatch.setenv("NWCWT_SHORT3", "1")
+    NWCWT_SHORT3=0 (read when the plan is created) switches the path off."""
     n = 1500
     fam = orc.Family("morlet", sfreq=1000, sigma=7.)
     fr = np.arange(1, 101.0)
