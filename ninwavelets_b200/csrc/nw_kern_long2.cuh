@@ -17,7 +17,10 @@ template <int CFG> struct Cfg2;
 template <> struct Cfg2<0> { static const int maxreg = NW_CFG0_MAXREG; };   // 256 x 3 (fp64: 168 registers, 128 x 3)
 template <> struct Cfg2<1> { static const int maxreg = 96; };               // 224 x 3
 template <> struct Cfg2<2> { static const int maxreg = 96; };               // 128 x 5
-template <> struct Cfg2<3> { static const int maxreg = 128; };              //  64 x 8
+#ifndef NW_CFG3_MAXREG
+#define NW_CFG3_MAXREG 128
+#endif
+template <> struct Cfg2<3> { static const int maxreg = NW_CFG3_MAXREG; };   //  64 x 8 (96 registers: 64 x 10)
 
 template <typename T, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2_kernel(const __grid_constant__ Long2Params<T> P) {

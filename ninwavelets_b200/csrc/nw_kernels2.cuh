@@ -253,14 +253,51 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     if (2 * nk1 >= N1) {
         // wide band (the decimated transforms of resampled rows): one sweep over the whole tile - row k1 holds the bin of
         // the window [k1lo, k1lo + N1) that is congruent to it, or zero (passA2_bins checks the band)
-        for (int i = tid; i < (N1 << tpsh); i += nthr) {
-            const int tp = i & (TP - 1);
-            const int k1 = i >> tpsh;
-            int u = k1 - k1lo;             // |k1lo| <= N1: u in (-N1, 2 N1)
-            if (u < 0) u += N1;
-            if (u >= N1) u -= N1;
-            const int pos = P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
-            buf[((size_t)pos << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1lo + u, c + 2 * tp);
+        const int total = N1 << tpsh;
+        if (P.sp.wtab) {
+            // tabulated weights: four slots per thread and trip, every load (slot position, two bins of X, two weights)
+            // issued before the first use - the sweep is one global-memory round trip per four slots instead of one per
+            // slot (ncu r02: long-scoreboard stalls dominate this kernel at two resident warps per CTA)
+            const T* wt = P.sp.wtab + rec.woff - rec.lo;
+            const cx<T>* Xs = X + rec.shift;
+            const cx<T> z0 = mk<T>((T)0, (T)0);
+            for (int i0 = tid; i0 < total; i0 += 4 * nthr) {
+                cx<T> xa[4], xb[4];
+                T wa[4], wb[4];
+                int pos[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + q * nthr;
+                    const bool v = i < total;
+                    const int k1 = i >> tpsh, k2 = c + 2 * (i & (TP - 1));
+                    int u = k1 - k1lo;
+                    if (u < 0) u += N1;
+                    if (u >= N1) u -= N1;
+                    const int j = (k1lo + u) * N2 + k2;
+                    const bool oa = v && k2 < N2 && j >= rec.lo && j < rec.hi;
+                    const bool ob = v && k2 + 1 < N2 && j + 1 >= rec.lo && j + 1 < rec.hi;
+                    pos[q] = !v ? 0 : P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
+                    xa[q] = oa ? Xs[j] : z0;
+                    wa[q] = oa ? wt[j] : (T)0;
+                    xb[q] = ob ? Xs[j + 1] : z0;
+                    wb[q] = ob ? wt[j + 1] : (T)0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + q * nthr;
+                    if (i < total) buf[((size_t)pos[q] << tpsh) + (i & (TP - 1))] = mk2<T>(scale(xa[q], wa[q]), scale(xb[q], wb[q]));
+                }
+            }
+        } else {
+            for (int i = tid; i < total; i += nthr) {
+                const int tp = i & (TP - 1);
+                const int k1 = i >> tpsh;
+                int u = k1 - k1lo;             // |k1lo| <= N1: u in (-N1, 2 N1)
+                if (u < 0) u += N1;
+                if (u >= N1) u -= N1;
+                const int pos = P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
+                buf[((size_t)pos << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1lo + u, c + 2 * tp);
+            }
         }
         NW_SYNC();
         if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
