@@ -21,15 +21,16 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"] + os.environ.get("NW_EXTRA_NVCC_FLAGS", "").split()
 
 
-def _deps():
-    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+def _deps(src=None):
+    """Files an object depends on: every header of csrc, the public header and its own .cu (all .cu files for the library)."""
+    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu") or src is None or f == src]
     d.append(os.path.join(os.path.dirname(HERE), "include", "nwcwt.h"))
     return d
 
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
-    newest = max(os.path.getmtime(d) for d in _deps())
+    newest = max(os.path.getmtime(d) for d in _deps(src))
     if os.path.isfile(obj) and os.path.getmtime(obj) >= newest:
         return obj, ""
     cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
@@ -43,9 +44,9 @@ def _compile(src, verbose):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    newest = max(os.path.getmtime(d) for d in _deps())
-    if not force and os.path.isfile(LIB) and os.path.getmtime(LIB) >= newest:
-        return LIB
+    if not force and os.path.isfile(LIB) and not os.path.isdir(OBJ):   # a shipped library without its objects: trust its date
+        if os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in _deps()):
+            return LIB
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
@@ -55,6 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
+    if os.path.isfile(LIB) and all(os.path.getmtime(o) <= os.path.getmtime(LIB) for o, _ in results):
+        return LIB                                                      # every object is older than the library
     cmd = [os.environ.get("NVCC", "nvcc"), "-shared", "-o", LIB] + [o for o, _ in results]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:

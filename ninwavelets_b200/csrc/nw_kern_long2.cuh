@@ -18,9 +18,9 @@ template <> struct Cfg2<0> { static const int maxreg = NW_CFG0_MAXREG; };   // 2
 template <> struct Cfg2<1> { static const int maxreg = 96; };               // 224 x 3
 template <> struct Cfg2<2> { static const int maxreg = 96; };               // 128 x 5
 #ifndef NW_CFG3_MAXREG
-#define NW_CFG3_MAXREG 128
+#define NW_CFG3_MAXREG 96
 #endif
-template <> struct Cfg2<3> { static const int maxreg = NW_CFG3_MAXREG; };   //  64 x 8 (96 registers: 64 x 10)
+template <> struct Cfg2<3> { static const int maxreg = NW_CFG3_MAXREG; };   //  64 x 10 (128 registers, 64 x 8: cfg2 6.82 vs 6.78 ms)
 
 template <typename T, int CFG, int SP>
 __global__ void __maxnreg__(Cfg2<CFG>::maxreg) nwcwt_passA2_kernel(const __grid_constant__ Long2Params<T> P) {

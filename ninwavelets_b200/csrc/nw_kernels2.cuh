@@ -194,6 +194,56 @@ NW_HD cx2<T> passA2_bins(const Long2Params<T>& P, const FreqRec& rec, int fi, co
     return mk2<T>(a, b);
 }
 
+// The gather of a tile with tabulated weights, four slots per thread and trip, every load (slot position, two bins of X,
+// two weights) issued before the first use: one global-memory round trip per four slots instead of one per slot (ncu r02:
+// long-scoreboard stalls dominated pass A at two resident warps per CTA; cfg2 7.31 -> 6.82 ms per step).
+//   WIDE:  element i is slot row k1 = i >> tpsh, which holds the row of the window [k1lo, k1lo + N1) congruent to it
+//   !WIDE: element i is signed row k1s = k1lo + (i >> tpsh) of the band's own rows, slot row k1s mod N1
+template <typename T, bool WIDE>
+NW_HD void passA2_gather4(const Long2Params<T>& P, const FreqRec& rec, const cx<T>* X, cx2<T>* buf, int total, int k1lo, int c,
+                          int tid, int nthr) {
+    const int tpsh = P.tpshA, TP = 1 << tpsh, N1 = P.N1, N2 = P.N2;
+    const T* wt = P.sp.wtab + rec.woff - rec.lo;
+    const cx<T>* Xs = X + rec.shift;
+    const cx<T> z0 = mk<T>((T)0, (T)0);
+    for (int i0 = tid; i0 < total; i0 += 4 * nthr) {
+        cx<T> xa[4], xb[4];
+        T wa[4], wb[4];
+        int pos[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * nthr;
+            const bool v = i < total;
+            const int k2 = c + 2 * (i & (TP - 1));
+            int k1, k1s;
+            if (WIDE) {
+                k1 = i >> tpsh;
+                int u = k1 - k1lo;             // |k1lo| <= N1: u in (-N1, 2 N1)
+                if (u < 0) u += N1;
+                if (u >= N1) u -= N1;
+                k1s = k1lo + u;
+            } else {
+                k1s = k1lo + (i >> tpsh);
+                k1 = k1s % N1;
+                if (k1 < 0) k1 += N1;
+            }
+            const int j = k1s * N2 + k2;
+            const bool oa = v && k2 < N2 && j >= rec.lo && j < rec.hi;
+            const bool ob = v && k2 + 1 < N2 && j + 1 >= rec.lo && j + 1 < rec.hi;
+            pos[q] = !v ? 0 : P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
+            xa[q] = oa ? Xs[j] : z0;
+            wa[q] = oa ? wt[j] : (T)0;
+            xb[q] = ob ? Xs[j + 1] : z0;
+            wb[q] = ob ? wt[j + 1] : (T)0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * nthr;
+            if (i < total) buf[((size_t)pos[q] << tpsh) + (i & (TP - 1))] = mk2<T>(scale(xa[q], wa[q]), scale(xb[q], wb[q]));
+        }
+    }
+}
+
 // The tile's input - spectrum x signal spectrum on the non-zero band only - is gathered into the
 // transform's shared-memory slots by a compact loop (one evaluation per in-band bin, nothing unrolled
 // around the formula), the rest of the tile is zero.
@@ -221,6 +271,51 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         // has at most ONE non-zero input, so the pass needs no zero fill, no gather and no loads: evaluate that one
         // product y = W_f(k) X[k] (if any) and write its R outputs  y * (w_R^q)^j,  j = 0..R-1.
         const int rl = P.stA.radix[P.stA.nst - 1], step = N1 / rl;
+        if (P.sp.wtab) {
+            // tabulated weights: four products per thread and trip, their loads (two bins of X, two weights, the twiddle)
+            // issued before the first use (as passA2_gather4)
+            const T* wt = P.sp.wtab + rec.woff - rec.lo;
+            const cx<T>* Xs = X + rec.shift;
+            const cx<T> z0 = mk<T>((T)0, (T)0);
+            const int total = step << tpsh;
+            for (int i0 = tid; i0 < total; i0 += 4 * nthr) {
+                cx<T> xa[4], xb[4], wq[4];
+                T wa[4], wb[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + q * nthr;
+                    const int k2 = c + 2 * (i & (TP - 1));
+                    const int rev = fft2_rev(P.stA, i >> tpsh);
+                    const uint32_t d = (uint32_t)(rev - k1lo + N1);
+                    const int u = (int)(d - fd_div(d, P.dstepA) * (uint32_t)step);
+                    const bool ok = i < total && u < nk1;
+                    const int k1s = k1lo + u;
+                    int k1 = k1s % N1;
+                    if (k1 < 0) k1 += N1;
+                    const int j = k1s * N2 + k2;
+                    const bool oa = ok && k2 < N2 && j >= rec.lo && j < rec.hi;
+                    const bool ob = ok && k2 + 1 < N2 && j + 1 >= rec.lo && j + 1 < rec.hi;
+                    xa[q] = oa ? Xs[j] : z0;
+                    wa[q] = oa ? wt[j] : (T)0;
+                    xb[q] = ob ? Xs[j + 1] : z0;
+                    wb[q] = ob ? wt[j + 1] : (T)0;
+                    wq[q] = ok ? P.twA[k1 - rev] : mk<T>((T)1, (T)0);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + q * nthr;
+                    if (i >= total) break;
+                    cx2<T>* e = buf + (((size_t)(i >> tpsh) * rl) << tpsh) + (i & (TP - 1));
+                    cx2<T> y = mk2<T>(scale(xa[q], wa[q]), scale(xb[q], wb[q]));
+                    e[0] = y;
+#pragma unroll 4
+                    for (int j = 1; j < rl; ++j) {
+                        y = cmul_s(y, wq[q]);
+                        e[(size_t)j << tpsh] = y;
+                    }
+                }
+            }
+        } else
         for (int i = tid; i < (step << tpsh); i += nthr) {
             const int tp = i & (TP - 1);
             const int blk = i >> tpsh;
@@ -255,39 +350,7 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
         // the window [k1lo, k1lo + N1) that is congruent to it, or zero (passA2_bins checks the band)
         const int total = N1 << tpsh;
         if (P.sp.wtab) {
-            // tabulated weights: four slots per thread and trip, every load (slot position, two bins of X, two weights)
-            // issued before the first use - the sweep is one global-memory round trip per four slots instead of one per
-            // slot (ncu r02: long-scoreboard stalls dominate this kernel at two resident warps per CTA)
-            const T* wt = P.sp.wtab + rec.woff - rec.lo;
-            const cx<T>* Xs = X + rec.shift;
-            const cx<T> z0 = mk<T>((T)0, (T)0);
-            for (int i0 = tid; i0 < total; i0 += 4 * nthr) {
-                cx<T> xa[4], xb[4];
-                T wa[4], wb[4];
-                int pos[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = i0 + q * nthr;
-                    const bool v = i < total;
-                    const int k1 = i >> tpsh, k2 = c + 2 * (i & (TP - 1));
-                    int u = k1 - k1lo;
-                    if (u < 0) u += N1;
-                    if (u >= N1) u -= N1;
-                    const int j = (k1lo + u) * N2 + k2;
-                    const bool oa = v && k2 < N2 && j >= rec.lo && j < rec.hi;
-                    const bool ob = v && k2 + 1 < N2 && j + 1 >= rec.lo && j + 1 < rec.hi;
-                    pos[q] = !v ? 0 : P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
-                    xa[q] = oa ? Xs[j] : z0;
-                    wa[q] = oa ? wt[j] : (T)0;
-                    xb[q] = ob ? Xs[j + 1] : z0;
-                    wb[q] = ob ? wt[j + 1] : (T)0;
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = i0 + q * nthr;
-                    if (i < total) buf[((size_t)pos[q] << tpsh) + (i & (TP - 1))] = mk2<T>(scale(xa[q], wa[q]), scale(xb[q], wb[q]));
-                }
-            }
+            passA2_gather4<T, true>(P, rec, X, buf, total, k1lo, c, tid, nthr);
         } else {
             for (int i = tid; i < total; i += nthr) {
                 const int tp = i & (TP - 1);
@@ -307,13 +370,17 @@ NW_HD void passA2_body(const Long2Params<T>& P, char* smem, int bx, int by, int 
     const cx2<T> z = zero2<T>();
     for (int i = tid; i < (N1 << tpsh); i += nthr) buf[i] = z;
     NW_SYNC();
-    for (int i = tid; i < (nk1 << tpsh); i += nthr) {
-        const int tp = i & (TP - 1);
-        const int k1s = k1lo + (i >> tpsh);
-        int k1 = k1s % N1;
-        if (k1 < 0) k1 += N1;
-        const int pos = P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
-        buf[((size_t)pos << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1s, c + 2 * tp);
+    if (P.sp.wtab) {
+        passA2_gather4<T, false>(P, rec, X, buf, nk1 << tpsh, k1lo, c, tid, nthr);
+    } else {
+        for (int i = tid; i < (nk1 << tpsh); i += nthr) {
+            const int tp = i & (TP - 1);
+            const int k1s = k1lo + (i >> tpsh);
+            int k1 = k1s % N1;
+            if (k1 < 0) k1 += N1;
+            const int pos = P.ditpos ? P.ditpos[k1] : fft2_dit_pos(P.stA, k1);
+            buf[((size_t)pos << tpsh) + tp] = passA2_bins<T>(P, rec, fi, X, k1s, c + 2 * tp);
+        }
     }
     NW_SYNC();
     if constexpr (SP == 0) fft2_dit<T, +1>(P.stA, tpsh, P.twA, buf, FromBuf(), dst, tid, nthr);
@@ -329,13 +396,23 @@ NW_HD void passA2f_body(const Long2Params<T>& P, char* smem, int bx, int by, int
     const int c = bx << (tpsh + 1);
     const int N1 = P.N1, N2 = P.N2;
     const T* x = P.signal + (size_t)(P.row0 + by) * (size_t)P.N;
-    for (int i = tid; i < (N1 << tpsh); i += nthr) {
-        const int tp = i & (TP - 1);
-        const int k1 = i >> tpsh;
-        const int k2 = c + 2 * tp;
-        const size_t k = (size_t)k1 * N2 + k2;
-        const T a = k2 < N2 ? x[k] : (T)0, b = k2 + 1 < N2 ? x[k + 1] : (T)0;
-        buf[((size_t)fft2_dit_pos(P.stA, k1) << tpsh) + tp] = mk2<T>(pk_make(a, b), pk_bcast((T)0));
+    const int total = N1 << tpsh;
+    for (int i0 = tid; i0 < total; i0 += 4 * nthr) {   // four slots per trip, the loads issued first (as passA2_gather4)
+        T a[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * nthr;
+            const int k2 = c + 2 * (i & (TP - 1));
+            const size_t k = (size_t)(i >> tpsh) * N2 + k2;
+            a[q] = (i < total && k2 < N2) ? x[k] : (T)0;
+            b[q] = (i < total && k2 + 1 < N2) ? x[k + 1] : (T)0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * nthr;
+            if (i < total)
+                buf[((size_t)fft2_dit_pos(P.stA, i >> tpsh) << tpsh) + (i & (TP - 1))] = mk2<T>(pk_make(a[q], b[q]), pk_bcast((T)0));
+        }
     }
     NW_SYNC();
     TmDst2<T, -1> dst{&P, P.Tm + (size_t)by * P.tm_stride, c};

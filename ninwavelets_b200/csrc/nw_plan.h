@@ -363,8 +363,8 @@ inline int ilog2_floor(long long v) { int l = 0; while ((1LL << (l + 1)) <= v) +
 // shape with more registers per thread.
 static const int N_CFG2 = 4;
 static const int CFG2_MAXTHR[N_CFG2] = {256, 224, 128, 64};
-static const int CFG2_MINCTA[N_CFG2] = {3, 3, 5, 8};
-static const int CFG2_MAXREG[N_CFG2] = {80, 96, 96, 128};   // __maxnreg__ of the compiled kernels
+static const int CFG2_MINCTA[N_CFG2] = {3, 3, 5, 10};
+static const int CFG2_MAXREG[N_CFG2] = {80, 96, 96, 96};   // __maxnreg__ of the compiled kernels
 inline int cfg2_regcap(int c) { return CFG2_MAXREG[c]; }
 
 inline void pick_threads2(const Fft2Plan& st, int tpsh, size_t smem, int ncfg, int& nthr, int& cfg) {

@@ -233,6 +233,15 @@ struct nwcwt_plan {
     size_t h_in_bytes = 0, h_out_bytes = 0, h_ws_bytes = 0;
     long long h_chunk = 0;
     cudaStream_t h_stream[2] = {nullptr, nullptr};
+    // CUDA-graph replay of the fast long path (nwcwt_transform): one step's launches - forward pairs, then per launch group
+    // pass A / pass B / interpolation on the forked auxiliary streams - are captured once per argument set and replayed
+    struct GraphEntry {
+        const void* signals; void* out; long long S; int output, bl; long long lo, hi; void* ws; size_t ws_bytes; int flags;
+        cudaGraphExec_t exec; long long launches; unsigned long long used;
+    };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;
+    unsigned long long graph_clock = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1125,6 +1134,80 @@ static int check_args(const nwcwt_plan* pl, int output, int bl, long long& blo, 
     return 0;
 }
 
+// Graph replay of nwcwt_transform on the fast long path.  The launch sequence of a call depends only on the plan and on the
+// call's arguments, so it is recorded once (stream capture on a stream of the plan; the auxiliary streams join the capture
+// through the fork event) and replayed with one cudaGraphLaunch into the caller's stream: kernel-to-kernel dependencies are
+// resolved on the device instead of through ~300 host launches and ~200 event calls per step.  A handful of argument sets is
+// kept per plan (least recently used goes first); an argument set is recorded the second time it is seen.  Returns 1 when
+// the call is not eligible or capture is unavailable (the caller then launches directly), 0 on success, a negative
+// NWCWT_ERR_* code on failure.  NWCWT_GRAPH=0 switches it off.
+static const int GRAPH_SLOTS = 4;
+template <typename T>
+static int transform_graph(nwcwt_plan* pl, const void* signals, void* out, long long S, int output, int bl, long long lo,
+                           long long hi, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    static const int use_graph = env_int("NWCWT_GRAPH", 1);
+    if (!use_graph || g_profile || pl->hp.path != 1 || !pl->hp.fast || g_force_generic || pl->n_aux < 2 || pl->l2_persist_max)
+        return 1;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return 1;                                   // the caller is capturing its own graph: launch into it directly
+    }
+    const int flags = (g_exact ? 1 : 0) | (g_no_static ? 2 : 0) | (g_rs_dir ? 4 : 0);
+    nwcwt_plan::GraphEntry* hit = nullptr;
+    for (nwcwt_plan::GraphEntry& g : pl->graphs)
+        if (g.signals == signals && g.out == out && g.S == S && g.output == output && g.bl == bl && g.lo == lo && g.hi == hi &&
+            g.ws == ws && g.ws_bytes == ws_bytes && g.flags == flags) { hit = &g; break; }
+    if (!hit) {
+        // first call with these arguments: remember them and launch directly - one-off calls never pay for a capture; the
+        // second identical call (a processing loop that reuses its buffers) records the graph, later ones replay it
+        if ((int)pl->graphs.size() >= GRAPH_SLOTS) {
+            size_t victim = 0;
+            for (size_t i = 1; i < pl->graphs.size(); ++i) if (pl->graphs[i].used < pl->graphs[victim].used) victim = i;
+            if (pl->graphs[victim].exec) cudaGraphExecDestroy(pl->graphs[victim].exec);
+            pl->graphs.erase(pl->graphs.begin() + (long)victim);
+        }
+        pl->graphs.push_back(nwcwt_plan::GraphEntry{signals, out, S, output, bl, lo, hi, ws, ws_bytes, flags, nullptr, 0, ++pl->graph_clock});
+        return 1;
+    }
+    if (hit->launches < 0) return 1;                 // capture failed before for this argument set
+    if (!hit->exec) {
+        hit->launches = -1;
+        if (!pl->cap_stream && cudaStreamCreateWithFlags(&pl->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        const long long l0 = g_launches.load();
+        if (cudaStreamBeginCapture(pl->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        const int rc = launch_long<T>(pl, signals, out, nullptr, S, output, bl, lo, hi, ws, ws_bytes, pl->cap_stream, false);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(pl->cap_stream, &graph);
+        const long long launches = g_launches.load() - l0;
+        g_launches.fetch_sub(launches);              // nothing ran yet: replays are counted below
+        if (rc || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc ? rc : 1;
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess || !exec) {
+            cudaGetLastError();
+            return 1;
+        }
+        hit->exec = exec;
+        hit->launches = launches;
+    }
+    hit->used = ++pl->graph_clock;
+    CUDA_TRY(cudaGraphLaunch(hit->exec, stream));
+    g_launches.fetch_add(hit->launches, std::memory_order_relaxed);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------
@@ -1305,6 +1388,13 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
         nwcwt_plan_destroy(g.sub);
     }
     pl->groups.clear();
+    if (!pl->graphs.empty() || pl->cap_stream) {
+        cudaSetDevice(pl->hp.device);
+        for (nwcwt_plan::GraphEntry& g : pl->graphs) cudaGraphExecDestroy(g.exec);
+        pl->graphs.clear();
+        if (pl->cap_stream) cudaStreamDestroy(pl->cap_stream);
+        pl->cap_stream = nullptr;
+    }
     if (pl->blu_f) nwcwt_plan_destroy(pl->blu_f);
     if (pl->blu_i) nwcwt_plan_destroy(pl->blu_i);
     pl->blu_f = pl->blu_i = nullptr;
@@ -1518,8 +1608,11 @@ int nwcwt_transform(nwcwt_plan* pl, const void* signals, void* out, int64_t S, i
     if (S <= 0) return 0;
     DeviceGuard guard(pl->hp.device);
     if ((rc = ensure_device(pl))) return rc;
-    if (pl->hp.dtype == NWCWT_F32)
+    if (pl->hp.dtype == NWCWT_F32) {
+        if ((rc = transform_graph<float>(pl, signals, out, S, output, bl, lo, hi, ws, ws_bytes, (cudaStream_t)stream)) <= 0) return rc;
         return run_transform<float>(pl, signals, out, nullptr, S, output, bl, lo, hi, ws, ws_bytes, (cudaStream_t)stream, false);
+    }
+    if ((rc = transform_graph<double>(pl, signals, out, S, output, bl, lo, hi, ws, ws_bytes, (cudaStream_t)stream)) <= 0) return rc;
     return run_transform<double>(pl, signals, out, nullptr, S, output, bl, lo, hi, ws, ws_bytes, (cudaStream_t)stream, false);
 }
 

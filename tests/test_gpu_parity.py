@@ -535,3 +535,43 @@ def test_resampled_short_rows_cfg3_slice(nw, mode, monkeypatch):
         assert l2_rel_err(a.reshape(-1, n).astype(np.float64), np.sqrt(ref).reshape(-1, n)).max() <= F32_TOL
     print("short resampled rows, baseline %s: worst row %.3e, vs exact kernel %.3e, groups %s" % (
         mode, e.max(), d, [(g["D"], g["K"], g["rows"]) for g in groups]))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_graph_replay_matches_direct_launches(nw, dtype):
+    """nwcwt_transform on the fast long path: the first call with an argument set launches directly, the second records a CUDA
+    graph, later ones replay it.  Replays must give the direct launches' bits, count the same launches, and read the
+    buffers' CURRENT contents (nothing of the data is baked into the graph)."""
+    import torch
+    from ninwavelets_b200 import _backend as be
+    n, fr = 60000, np.arange(2, 42.0)
+    obj = make(nw, "morse", dict(sfreq=1000), dtype=dtype)
+    obj.make_fft_wavelets(fr, n / 1000.0)
+    plan = obj._plan
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((3, n), device="cuda", dtype=tdt, generator=g)
+    out = torch.empty((3, len(fr), n), device="cuda", dtype=tdt)
+    l0 = be.launch_count()
+    plan.transform_device(x, be.OUT_POWER, out=out)          # direct launches
+    n_direct = be.launch_count() - l0
+    direct = out.clone()
+    counts = []
+    for _ in range(3):                                        # records, then replays
+        out.zero_()
+        l0 = be.launch_count()
+        plan.transform_device(x, be.OUT_POWER, out=out)
+        counts.append(be.launch_count() - l0)
+        assert torch.equal(out, direct)
+    assert counts == [n_direct] * 3 and n_direct > 3
+    x.copy_(torch.randn((3, n), device="cuda", dtype=tdt, generator=g))
+    plan.transform_device(x, be.OUT_POWER, out=out)          # replay on new data in the same buffers
+    fresh = plan.transform_device(x.clone(), be.OUT_POWER)   # new argument set: direct launches
+    assert torch.equal(out, fresh)
+    xs = x[0].double().cpu().numpy()
+    ref = orc.power(orc.Family("morse", sfreq=1000), xs, fr)
+    got = out[0].double().cpu().numpy()
+    if dtype == "float32":
+        assert l2_rel_err(got, ref).max() <= F32_TOL
+    else:
+        assert peak_rel_err(got, ref).max() <= F64_TOL
