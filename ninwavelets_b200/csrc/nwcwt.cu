@@ -1390,7 +1390,7 @@ int nwcwt_plan_destroy(nwcwt_plan* pl) {
     pl->groups.clear();
     if (!pl->graphs.empty() || pl->cap_stream) {
         cudaSetDevice(pl->hp.device);
-        for (nwcwt_plan::GraphEntry& g : pl->graphs) cudaGraphExecDestroy(g.exec);
+        for (nwcwt_plan::GraphEntry& g : pl->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);   // exec is null for a set seen once
         pl->graphs.clear();
         if (pl->cap_stream) cudaStreamDestroy(pl->cap_stream);
         pl->cap_stream = nullptr;

@@ -11,7 +11,7 @@ import sys
 from collections import OrderedDict
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "..", "..", "gpurun_out", "r02")
+SRC = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "..", "..", "gpurun_out", "r02b")
 
 
 def bench_lines():
@@ -72,7 +72,7 @@ def summarise_launches(ls, per_step):
     rd = sum(a["rd"] for a in agg.values())
     wr = sum(a["wr"] for a in agg.values())
     md = ["# r02 - ncu launch list of `python bench.py --steps 1 --warmup 3 --tuning` (cfg2, fp32), one step = %d launches\n" % per_step,
-          "`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none`;",
+          "`NWCWT_GRAPH=0 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none`\n(graph replay off under ncu: the same kernels, launched from the host);",
           "per-launch times under ncu are serialised (no overlap between the plan's streams), so the SHARES are what compares with the",
           "bench line's `roofline.single_stream.classes_ms`; the full list is `launches_bench_cfg2_r02.csv.gz`.\n",
           "| kernel | launches | sum us | share | avg us | DRAM read MB | DRAM write MB |", "|---|---|---|---|---|---|---|"]
@@ -87,6 +87,7 @@ def summarise_launches(ls, per_step):
 def ncu_tables():
     for rep, dst in (("ncu_cfg2_rs", "ncu_cfg2_summary.md"), ("ncu_cfg3", "ncu_cfg3_summary.md")):
         raws = [os.path.join(SRC, r + ".raw.csv") for r in ((rep, "ncu_cfg2_ab") if rep == "ncu_cfg2_rs" else (rep,))]
+        # (the cfg3 kernel did not change after the first pass of the round: its capture is not repeated)
         raws = [r for r in raws if os.path.isfile(r) and os.path.getsize(r) > 0]
         if not raws:
             continue

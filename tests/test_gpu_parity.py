@@ -575,3 +575,25 @@ def test_graph_replay_matches_direct_launches(nw, dtype):
         assert l2_rel_err(got, ref).max() <= F32_TOL
     else:
         assert peak_rel_err(got, ref).max() <= F64_TOL
+
+
+def test_plan_close_leaves_no_cuda_error_behind(nw):
+    """A plan whose graph cache holds argument sets that were only seen once (no recorded graph) is destroyed; the next
+    launches - the host-buffer entry point of another plan, whose kernels check cudaGetLastError - must not see a stale
+    CUDA error (r02: cudaGraphExecDestroy(nullptr) left 'invalid argument' for bench.py's end-to-end leg)."""
+    import torch
+    from ninwavelets_b200 import _backend as be
+    n, fr = 60000, np.array([3.0, 17.0, 40.0])
+    a = make(nw, "morse", dict(sfreq=1000), dtype="float32")
+    a.make_fft_wavelets(fr, n / 1000.0)
+    b = make(nw, "morse", dict(sfreq=1000), dtype="float32")
+    b.make_fft_wavelets(fr, n / 1000.0)
+    x = torch.randn((2, n), device="cuda", dtype=torch.float32)
+    a._plan.transform_device(x, be.OUT_POWER)        # one-off argument sets: remembered, never recorded
+    a._plan.transform_device(x[:1], be.OUT_POWER)
+    torch.cuda.synchronize()
+    a._plan.close()
+    hx = np.random.default_rng(4).standard_normal((2, n)).astype(np.float32)
+    got = b._plan.transform_host(hx, be.OUT_POWER)
+    ref = orc.power(orc.Family("morse", sfreq=1000), hx[1].astype(np.float64), fr)
+    assert l2_rel_err(got[1].astype(np.float64), ref).max() <= F32_TOL
