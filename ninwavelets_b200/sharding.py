@@ -40,7 +40,7 @@ def gather_blocks(local, axis: int, counts, group=None):
     return torch.cat([o.narrow(axis, 0, c) for o, c in zip(outs, counts)], dim=axis)
 
 
-def distributed_transform(local_fn: Callable, signals: np.ndarray, freqs, *, gather: bool = True, group=None,
+def distributed_transform(local_fn: Callable, signals, freqs, *, gather: bool = True, group=None,
                           rank: Optional[int] = None, world: Optional[int] = None):
     """Run `local_fn(signals_block, freqs_block) -> [s, f, n]` on this rank's shard.
 
@@ -54,7 +54,8 @@ def distributed_transform(local_fn: Callable, signals: np.ndarray, freqs, *, gat
         world = dist.get_world_size(group) if dist.is_initialized() else 1
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
-    signals = np.asarray(signals)
+    if not hasattr(signals, "shape"):   # numpy arrays, torch tensors (host or device resident) and array-likes with shape + slicing pass through
+        signals = np.asarray(signals)
     freqs = np.asarray(freqs, dtype=np.float64)
     S, F = signals.shape[0], len(freqs)
     axis_name = shard_axis(S, F, world)

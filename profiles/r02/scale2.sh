@@ -17,8 +17,10 @@ except Exception as e:
     print("$name: failed", e, open("$O/$name.err").read()[-800:])
 EOF
 }
+if [ "${ONLY:-all}" != strong ]; then
 run bench_1gpu_cfg2 python bench.py --gpus 1 --steps 10 --warmup 3 --tuning
 run bench_2gpu_weak_cfg2 $TR bench.py --gpus 2 --steps 10 --warmup 3 --tuning
+fi
 run bench_2gpu_strong_cfg2 $TR bench.py --gpus 2 --steps 10 --warmup 3 --tuning --scaling strong
 run bench_1gpu_strong_cfg5_20 python bench.py --gpus 1 --steps 3 --warmup 3 --tuning --scaling strong --workload cfg5_20
 run bench_2gpu_strong_cfg5_20 $TR bench.py --gpus 2 --steps 3 --warmup 3 --tuning --scaling strong --workload cfg5_20

@@ -63,3 +63,29 @@ def test_distributed_transform_gloo(world, S, F):
     for rank, shape, err in res:
         assert shape == (S, F, 300), (rank, shape)
         assert err < 1e-12, (rank, err)
+
+
+def test_distributed_transform_takes_resident_tensors_and_proxies():
+    """The driver must not pull its input through numpy: a torch tensor (device resident on a GPU box) or any object with
+    `.shape` and slicing (bench.py hands it a view of the rank's resident block) is sliced as it is."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((5, 300))
+    fr = np.arange(2.0, 7.0)
+    seen = []
+
+    def local(xs, f):
+        seen.append(type(xs))
+        return _local(np.asarray(xs), f)
+
+    for rank in range(2):
+        blk, axis, (lo, hi) = distributed_transform(local, torch.as_tensor(x), fr, gather=False, rank=rank, world=2)
+        assert axis == "signals" and np.allclose(blk.numpy(), _local(x[lo:hi], fr))
+    assert all(t is torch.Tensor for t in seen)
+
+    class Proxy:
+        shape = x.shape
+
+        def __getitem__(self, sl):
+            return x[sl]
+    blk, axis, (lo, hi) = distributed_transform(_local, Proxy(), fr, gather=False, rank=1, world=2)
+    assert (lo, hi) == shard_range(5, 1, 2) and np.allclose(blk.numpy(), _local(x[lo:hi], fr))
