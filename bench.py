@@ -463,9 +463,8 @@ def run_graft(args, wl):
 
     # ---- fp64 sibling (the reference's own arithmetic) on the same workload ------------------------
     fp64 = None
-    if f32 and not args.tuning and not strong and world == 1 and not n_ep and S_buf * F * N * 8 <= 75e9:
-        del out
-        torch.cuda.empty_cache()
+    try_fp64 = f32 and not args.tuning and not strong and world == 1 and not n_ep and S_buf * F * N * 8 <= 75e9
+    def fp64_leg():
         _, plan64 = make_plan("float64")
         x64 = x.double()
         out64 = torch.empty((S_buf, F, N), dtype=torch.float64, device=dev)
@@ -487,12 +486,21 @@ def run_graft(args, wl):
         ms64 = e0.elapsed_time(e1) / k64
         plan64.transform_device(x64[:1], be.OUT_POWER, *bl, out=out64[:1])
         torch.cuda.synchronize()
-        fp64 = {"value": S * F * N / (ms64 * 1e-3), "unit": UNIT, "ms_per_step": ms64, "steps": k64,
-                "roofline_frac_hbm": S * N * (F + 1) * 8 / (ms64 * 1e-3) / 1e9 / peak,
-                "parity_spot_check": spot_check(out64, hx[0], False),
-                "groups": [(g["D"], g["K"]) for g in plan64.info().get("groups", [])]}
+        res = {"value": S * F * N / (ms64 * 1e-3), "unit": UNIT, "ms_per_step": ms64, "steps": k64,
+               "roofline_frac_hbm": S * N * (F + 1) * 8 / (ms64 * 1e-3) / 1e9 / peak,
+               "parity_spot_check": spot_check(out64, hx[0], False),
+               "groups": [(g["D"], g["K"]) for g in plan64.info().get("groups", [])]}
         del out64, x64
         plan64.close()
+        return res
+
+    if try_fp64:
+        del out
+        torch.cuda.empty_cache()
+        try:   # a failure of a secondary leg is reported in the line, it does not take the headline measurement with it
+            fp64 = fp64_leg()
+        except Exception as e:
+            fp64 = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
         torch.cuda.empty_cache()
         out = torch.empty((S_buf, F, N), dtype=tdt, device=dev)
 
@@ -502,6 +510,7 @@ def run_graft(args, wl):
     elif F * N * real_b > (8 << 30):
         e2e = {"value": None, "unit": UNIT, "note": "one signal's output exceeds 8 GiB; host leg not run for this sweep size"}
     else:
+      try:
         e2e_S = min(S, max(1, int((16 << 30) // (F * N * real_b))))       # the whole job when its output fits 16 GiB of pinned memory
         host_out = torch.empty((e2e_S, F, N), dtype=tdt).pin_memory()
         hin = hx[:e2e_S]
@@ -523,6 +532,10 @@ def run_graft(args, wl):
                "steps": e2e_steps, "signals_per_step": e2e_S,
                "api": "nwcwt_transform_host (pinned host buffers; chunked H2D -> kernels -> D2H on two streams)",
                "note": "bound by the device-to-host copy of 4 B per output point over PCIe"}
+      except Exception as e:
+        if world > 1:   # the other ranks are waiting in the all-reduce: fail loudly rather than hang
+            raise
+        e2e = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
 
     cpu = None
     if rank == 0 and not args.tuning:
