@@ -188,7 +188,12 @@ int nwcwt_forward(nwcwt_plan* plan, const void* signals_dev, void* spectra_dev, 
  * frequencies (base.py:396-406 + :443 + :425 + Baseline :46-68).
  *   out_dev: [n_signals][n_freqs][n], real (ABS/POWER) or complex interleaved (CWT)
  *   baseline != NONE needs a real output; the window is [base_lo, base_hi) in samples,
- *   i.e. wave[int(start*sfreq):int(stop*sfreq)] (base.py:49). */
+ *   i.e. wave[int(start*sfreq):int(stop*sfreq)] (base.py:49).
+ * The call enqueues on `stream` and returns.  Long rows: the second call with the same arguments (buffers,
+ * n_signals, modes, workspace) records its launch sequence as a CUDA graph and later identical calls replay it
+ * with one cudaGraphLaunch - same kernels, same results, the buffers' current contents are read; a `stream`
+ * that is itself being captured gets the plain launches.  NWCWT_GRAPH=0 in the environment switches this off.
+ * A plan serves one stream / one host thread at a time (its workspace and auxiliary streams are shared state). */
 int nwcwt_transform(nwcwt_plan* plan, const void* signals_dev, void* out_dev, int64_t n_signals,
                     int32_t output, int32_t baseline, int64_t base_lo, int64_t base_hi,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
