@@ -1,5 +1,7 @@
 #!/bin/bash
 # generic A/B of two library builds on the same box: ninwavelets_b200/libnwcwt_prev.so (previous) vs libnwcwt.so (new)
+# (keep a copy of the current library as libnwcwt_prev.so before rebuilding; used for the stride-parameter experiment of
+#  experiments_r02.md)
 set -u
 O=gpurun_out/r02lib
 mkdir -p $O

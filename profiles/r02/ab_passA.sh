@@ -2,6 +2,8 @@
 # A/B of pass-A variants on cfg2 (and cfg4, cfg5_20): library builds side by side, selected with NWCWT_LIB.
 #   base: the build measured in bench_lines_r02.jsonl; (default): four-slot gather with the loads issued first;
 #   r96:  the same + 96-register cap for the 64-thread launch shape (10 instead of 8 resident CTAs per SM)
+# (historical: libnwcwt_base.so = the build of commit 762d80c, libnwcwt_r96.so = k_long2_f32_c3.cu compiled with
+#  -DNW_CFG3_MAXREG=96 and linked with the other objects; both were removed once the variant became the default)
 set -u
 O=gpurun_out/r02ab
 mkdir -p $O

@@ -2,7 +2,8 @@
 # r02 measurement pass on one B200 (run under gpurun from the repo root):
 #   gpurun --timeout 1500 -- 'bash profiles/r02/measure_final.sh'
 # Every ncu command runs only after the same program has exited 0 without ncu; numbers printed under ncu are never
-# bench values.  Results land in gpurun_out/r02/ and are summarised into profiles/r02/ by profiles/r02/collect.py.
+# bench values.  Results land in gpurun_out/r02b/ (first pass of the round: gpurun_out/r02/) and are summarised into
+# profiles/r02/ by profiles/r02/collect.py.
 set -u
 O=gpurun_out/r02b
 mkdir -p $O
