@@ -512,7 +512,7 @@ def run_graft(args, wl):
     else:
       try:
         e2e_S = min(S, max(1, int((16 << 30) // (F * N * real_b))))       # the whole job when its output fits 16 GiB of pinned memory
-        host_out = torch.empty((e2e_S, F, N), dtype=tdt).pin_memory()
+        host_out = torch.empty((e2e_S, F, N), dtype=tdt, pin_memory=True)   # allocated pinned (no pageable copy first)
         hin = hx[:e2e_S]
         hout = host_out.numpy()
         plan.transform_host(hin, be.OUT_POWER, *bl, out=hout)        # warm-up (allocates staging)
